@@ -1,0 +1,74 @@
+// Host-callable launchers of the ehb200 kernels (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "walk.cuh"
+
+namespace ehb {
+
+constexpr uint32_t kMaxDim = 2048;  // pad_dim() supports rows up to 2048 floats
+constexpr uint32_t kMaxEf = 512;    // register-resident list: 16 keys per lane
+
+// K2 — batched k-NN graph walk (hnswlib searchKnn).  ef >= k, cfg.lcap >= ef.
+// stats: [nq][4] u32 = hops_upper, hops_base, evals, overflow.
+cudaError_t launch_search(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
+                          uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                          uint32_t* stats, uint32_t warps_per_block, cudaStream_t s);
+
+// row-wise L2 normalisation (hnswlib cosine convention), canonical arithmetic.
+cudaError_t launch_normalize(const float* in, uint32_t in_stride, float* out, uint32_t out_stride, uint64_t n,
+                             uint32_t dim, cudaStream_t s);
+// copy [n][dim] -> [n][dpad] with zero padding (and optional normalisation)
+cudaError_t launch_pad_rows(const float* in, float* out, uint64_t n, uint32_t dim, uint32_t dpad, bool normalize,
+                            cudaStream_t s);
+cudaError_t launch_sum_stats(const uint32_t* stats, uint32_t nq, unsigned long long* out4, cudaStream_t s);
+
+// K1 — exact fp32 brute force with canonical arithmetic.
+struct BruteScratch {
+  float* dist;          // [qb][nc]
+  uint64_t* part_keys;  // [qb][slices][k]
+  uint64_t* run_keys;   // [nq][k] running best
+  uint64_t qb, nc, slices;
+};
+cudaError_t launch_bruteforce_exact(const float* vecs, uint32_t dpad, uint32_t dim, uint64_t n, const uint64_t* labels,
+                                    int metric, const float* queries /*[nq][dim]*/, uint64_t nq, uint32_t k,
+                                    BruteScratch& sc, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                                    cudaStream_t s);
+
+// K4 — merge of G sorted (dist,label) lists per query.
+cudaError_t launch_merge_topk(uint32_t G, uint64_t nq, uint32_t k, const float* dists, const uint64_t* labels,
+                              float* out_dists, uint64_t* out_labels, uint32_t* out_counts, cudaStream_t s);
+
+// K5 — batched graph construction.
+struct BuildBuffers {
+  // per-batch edge list (reverse links to apply)
+  uint32_t* edge_row;   // target row id (level-0 rows: node id; upper rows: cap + row)
+  uint32_t* edge_src;
+  float* edge_dist;
+  uint32_t* edge_count; // [1]
+  uint32_t edge_cap;
+  // per-row scratch, sized row_space = cap + upper_cap
+  uint32_t* row_cnt;
+  uint32_t* row_fill;
+  uint32_t* row_start;
+  uint32_t* touched;    // [edge_cap]
+  uint32_t* touched_count;  // [1]
+  uint32_t* seg_cursor;     // [1]
+  uint32_t* seg_src;    // [edge_cap]
+  float* seg_dist;      // [edge_cap]
+  uint32_t* error_flag; // [1]
+};
+struct BuildGraph {
+  GraphView g;          // links are written through these pointers (const-cast inside)
+  const uint8_t* levels;
+  const uint32_t* up_owner;  // [upper rows] owning node of each upper row
+  uint32_t cap;         // row id space split: rows >= cap are upper rows
+  uint32_t efc;
+};
+// Links points ids[0..b) (or first..first+b when ids == nullptr) into the graph.
+cudaError_t launch_build_batch(const BuildGraph& bg, const WalkCfg& cfg, const uint32_t* ids, uint32_t first,
+                               uint32_t b, bool is_update, BuildBuffers& bb, uint32_t warps_per_block,
+                               cudaStream_t s);
+
+}  // namespace ehb

@@ -1,0 +1,100 @@
+// K2 kernel template + launcher (included by the per-shape translation units).
+#pragma once
+#include "kernels.h"
+
+namespace ehb {
+
+template <int LPV, int NQ, int KPL>
+__global__ void __launch_bounds__(128) hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
+                                                          uint32_t nq, uint32_t k, uint32_t ef,
+                                                          uint64_t* __restrict__ out_labels,
+                                                          float* __restrict__ out_dists,
+                                                          uint32_t* __restrict__ out_counts,
+                                                          uint32_t* __restrict__ stats, uint32_t warp_smem) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t w = threadIdx.x >> 5;
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + w;
+  if (q >= nq) return;
+  WarpCtx c;
+  ctx_init(c, smem + (size_t)w * warp_smem, cfg, g.dpad);
+  float4 qr[NQ];
+  load_query_regs<LPV, NQ>(qr, queries + (size_t)q * g.dim, g.dim, c.lane);
+  WalkCounters wc = {0, 0, 0, 0};
+  uint64_t keys[KPL];
+  rl_clear<KPL>(keys);
+  if (g.n != 0) {
+    uint32_t cur = g.entry;
+    if (c.lane == 0) c.cand_id[0] = cur;
+    __syncwarp();
+    eval_candidates<LPV, NQ>(c, g.vecs, qr, 1, g.metric);
+    float curdist = c.cand_dist[0];
+    __syncwarp();
+    wc.evals = 1;
+    greedy_descent<LPV, NQ>(c, g, qr, cur, curdist, g.max_level, 0, wc);
+    beam_search<LPV, NQ, KPL, true>(c, g, qr, keys, cur, curdist, 0, ef, kInvalid, wc);
+  }
+  const uint32_t found = min(rl_count<KPL>(keys), k);
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    uint32_t i = (uint32_t)s * 32u + c.lane;
+    if (i < k) {
+      uint64_t lab = 0xFFFFFFFFFFFFFFFFull;
+      float d = INFINITY;
+      if (i < found) {
+        lab = g.labels[key_id(keys[s])];
+        d = key_dist(keys[s]);
+      }
+      out_labels[(size_t)q * k + i] = lab;
+      if (out_dists) out_dists[(size_t)q * k + i] = d;
+    }
+  }
+  if (c.lane == 0) {
+    if (out_counts) out_counts[q] = found;
+    if (stats) ((uint4*)stats)[q] = make_uint4(wc.hops_upper, wc.hops_base, wc.evals, wc.overflow);
+  }
+}
+
+template <int LPV, int NQ, int KPL>
+cudaError_t launch_search_t(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
+                            uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                            uint32_t* stats, uint32_t wpb, cudaStream_t s) {
+  uint32_t wsm = warp_smem_bytes(cfg, g.dpad);
+  size_t smem = (size_t)wsm * wpb;
+  dim3 grid((nq + wpb - 1) / wpb), block(32 * wpb);
+  auto kern = hnsw_search_kernel<LPV, NQ, KPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, block, smem, s>>>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wsm);
+  return cudaGetLastError();
+}
+
+template <int LPV, int NQ>
+cudaError_t launch_search_kpl(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
+                              uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                              uint32_t* stats, uint32_t wpb, cudaStream_t s) {
+#define EHB_KPL(K) \
+  return launch_search_t<LPV, NQ, K>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wpb, s)
+  if (ef <= 64) EHB_KPL(2);
+  if (ef <= 128) EHB_KPL(4);
+  if (ef <= 256) EHB_KPL(8);
+  EHB_KPL(16);
+#undef EHB_KPL
+}
+
+#define EHB_SEARCH_ARGS                                                                                       \
+  const GraphView &g, const WalkCfg &cfg, const float *queries, uint32_t nq, uint32_t k, uint32_t ef,         \
+      uint64_t *out_labels, float *out_dists, uint32_t *out_counts, uint32_t *stats, uint32_t wpb, cudaStream_t s
+#define EHB_SEARCH_PASS g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wpb, s
+
+cudaError_t launch_search_d32(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d64(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d128(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d256(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d384(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d512(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d768(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d1024(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d1536(EHB_SEARCH_ARGS);
+cudaError_t launch_search_d2048(EHB_SEARCH_ARGS);
+
+}  // namespace ehb

@@ -1,0 +1,512 @@
+// Warp-per-query HNSW graph walk machinery (device side).
+//
+// Replaces hnswlib's searchKnn / searchBaseLayerST / searchBaseLayer hot loops
+// (called from embeddinghub/embeddingstore/index.cc:36,41) with a design that
+// fits the B200 memory system:
+//   * one warp owns one query (or one point being inserted);
+//   * an adjacency row is one 128 B line (2M = 32 u32, padded with kInvalid);
+//   * hnswlib's ef-bounded result heap and its candidate heap are ONE sorted
+//     array of 64-bit keys (ordered distance | expanded flag | id) held in
+//     registers, KPL keys per lane, maintained with warp shuffles;
+//   * the visited set is a per-warp open-addressing table in shared memory;
+//   * distances of the unvisited neighbours of a node are evaluated together:
+//       - rows up to 1 KB (LPV = 8 lanes per vector): every lane issues its
+//         128-bit loads for up to 16 vectors before the first use, so a hop
+//         has 8 KB..16 KB in flight per warp straight into registers;
+//       - larger rows (LPV = 32): the TMA engine pulls whole rows HBM -> shared
+//         memory (cp.async.bulk, one bulk copy per vector, completion counted
+//         on an mbarrier) in a ring of groups, and the math on group r overlaps
+//         the copies of the following groups.
+//     (v1 staged every row through TMA; ncu showed the walk issue-bound with
+//      17 % of all issued instructions in the per-lane UBLKCP serialisation
+//      loops at d=128, see profiles/r01_walk_v1_summary.md.)
+//   * rows are padded to an exact multiple of the per-lane tile, so the inner
+//     loops carry no bounds checks.
+#pragma once
+#include "common.cuh"
+
+namespace ehb {
+
+struct GraphView {
+  const float* vecs;         // [n][dpad] fp32, rows 16 B aligned, zero padded
+  const uint32_t* links0;    // [n][M0]
+  const uint32_t* up_off;    // [n] first upper row of node i, kInvalid if level 0
+  const uint32_t* links_up;  // [rows][M]
+  const uint64_t* labels;    // [n]
+  uint32_t n, dim, dpad, M, M0, entry;
+  int32_t max_level;
+  int32_t metric;            // 0 = squared L2, 1 = 1 - dot (IP and cosine)
+};
+
+struct WalkCfg {
+  uint32_t lcap;       // shared-memory key list capacity (0 = none; cold paths only)
+  uint32_t hash_bits;  // log2(entries) of the visited table, 0 = none
+  uint32_t G;          // vectors per TMA staging group (<= 32), LPV = 32 only
+  uint32_t NG;         // staging groups (ring depth, <= 8)
+  uint32_t staged;     // 1 when the TMA staging ring is allocated
+};
+
+__host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+// Supported padded row lengths: LPV=8 -> NQ in {1,2,4,8}; LPV=32 -> NQ in {3,4,6,8,12,16}.
+__host__ __device__ inline uint32_t pad_dim(uint32_t dim) {
+  const uint32_t sizes[10] = {32, 64, 128, 256, 384, 512, 768, 1024, 1536, 2048};
+  for (int i = 0; i < 10; ++i)
+    if (dim <= sizes[i]) return sizes[i];
+  return 0;
+}
+
+// Per-warp shared-memory slice; every region offset is a multiple of 128 B.
+__host__ __device__ inline uint32_t warp_smem_bytes(const WalkCfg& c, uint32_t dpad) {
+  uint32_t b = 0;
+  b += align_up(c.lcap * 8u, 128);
+  b += align_up(c.hash_bits ? (4u << c.hash_bits) : 0u, 128);
+  b += 128;  // cand_id[32]
+  b += 128;  // cand_dist[32]
+  b += 128;  // mbarriers (<= 8) + spare
+  b += c.staged ? align_up(c.G * c.NG * dpad * 4u, 128) : 0u;
+  return b;
+}
+
+struct WarpCtx {
+  uint64_t* keys;
+  uint32_t* hash;
+  uint32_t* cand_id;
+  float* cand_dist;
+  uint64_t* mbar;
+  float* stage;
+  uint32_t lcap, hmask, hshift, G, NG, dpad, vbytes;
+  uint32_t phases;  // one parity bit per staging group
+  uint32_t cnt;     // live entries in keys[] (shared-memory list only)
+  uint32_t lane;
+};
+
+__device__ __forceinline__ void ctx_init(WarpCtx& c, unsigned char* base, const WalkCfg& cfg, uint32_t dpad) {
+  c.lane = lane_id();
+  c.lcap = cfg.lcap;
+  c.G = cfg.G;
+  c.NG = cfg.NG;
+  c.dpad = dpad;
+  c.vbytes = dpad * 4u;
+  c.hmask = cfg.hash_bits ? ((1u << cfg.hash_bits) - 1u) : 0u;
+  c.hshift = 32u - cfg.hash_bits;
+  unsigned char* p = base;
+  c.keys = (uint64_t*)p;
+  p += align_up(cfg.lcap * 8u, 128);
+  c.hash = (uint32_t*)p;
+  p += align_up(cfg.hash_bits ? (4u << cfg.hash_bits) : 0u, 128);
+  c.cand_id = (uint32_t*)p;
+  p += 128;
+  c.cand_dist = (float*)p;
+  p += 128;
+  c.mbar = (uint64_t*)p;
+  p += 128;
+  c.stage = (float*)p;
+  c.phases = 0;
+  c.cnt = 0;
+  if (cfg.staged) {
+    if (c.lane < cfg.NG) mbar_init(&c.mbar[c.lane], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void hash_clear(WarpCtx& c) {
+  uint4* h4 = (uint4*)c.hash;
+  uint32_t n4 = (c.hmask + 1u) >> 2;
+  for (uint32_t i = c.lane; i < n4; i += 32) h4[i] = make_uint4(kInvalid, kInvalid, kInvalid, kInvalid);
+  __syncwarp();
+}
+
+// Lane-parallel "test and set".  Returns true when id was not in the table
+// (and is now, unless the probe budget ran out -> overflow).
+__device__ __forceinline__ bool hash_insert(WarpCtx& c, uint32_t id, uint32_t& overflow) {
+  uint32_t h = (id * 0x9E3779B1u) >> c.hshift;
+#pragma unroll 1
+  for (int probe = 0; probe < 32; ++probe) {
+    uint32_t old = atomicCAS(&c.hash[h], kInvalid, id);
+    if (old == kInvalid) return true;
+    if (old == id) return false;
+    h = (h + 1u) & c.hmask;
+  }
+  overflow = 1;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Query / vector registers: lane `sub = lane % LPV` holds float4 chunks
+// sub + LPV*t, t < NQ  (dpad == 4 * LPV * NQ exactly).
+// ---------------------------------------------------------------------------
+template <int LPV, int NQ>
+__device__ __forceinline__ void load_query_regs(float4 (&qr)[NQ], const float* __restrict__ src, uint32_t dim,
+                                                uint32_t lane) {
+  uint32_t sub = lane % LPV;
+#pragma unroll
+  for (int t = 0; t < NQ; ++t) {
+    uint32_t e = (sub + LPV * t) * 4u;
+    float4 v;
+    v.x = e + 0 < dim ? src[e + 0] : 0.f;
+    v.y = e + 1 < dim ? src[e + 1] : 0.f;
+    v.z = e + 2 < dim ? src[e + 2] : 0.f;
+    v.w = e + 3 < dim ? src[e + 3] : 0.f;
+    qr[t] = v;
+  }
+}
+template <int LPV, int NQ>
+__device__ __forceinline__ void load_vec_regs(float4 (&r)[NQ], const float* __restrict__ row, uint32_t lane) {
+  const float4* r4 = (const float4*)row + (lane % LPV);
+#pragma unroll
+  for (int t = 0; t < NQ; ++t) r[t] = r4[LPV * t];
+}
+
+template <int NQ>
+__device__ __forceinline__ float partial_dist(const float4 (&v)[NQ], const float4 (&qr)[NQ], int metric) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (metric == 0) {
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      float dx = qr[t].x - v[t].x, dy = qr[t].y - v[t].y, dz = qr[t].z - v[t].z, dw = qr[t].w - v[t].w;
+      a0 = fmaf(dx, dx, a0);
+      a1 = fmaf(dy, dy, a1);
+      a2 = fmaf(dz, dz, a2);
+      a3 = fmaf(dw, dw, a3);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      a0 = fmaf(qr[t].x, v[t].x, a0);
+      a1 = fmaf(qr[t].y, v[t].y, a1);
+      a2 = fmaf(qr[t].z, v[t].z, a2);
+      a3 = fmaf(qr[t].w, v[t].w, a3);
+    }
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+template <int LPV>
+__device__ __forceinline__ float group_reduce(float acc) {
+#pragma unroll
+  for (int o = LPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+// ---- LPV = 8: direct 128-bit loads, U steps (4 vectors each) in flight ------
+template <int NQ>
+__device__ __forceinline__ void eval_direct(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
+                                            uint32_t m, int metric) {
+  constexpr int U = NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2);  // 64 registers of loads in flight
+  const uint32_t sub = c.lane & 7u, grp = c.lane >> 3;
+  __syncwarp();
+#pragma unroll 1
+  for (uint32_t j0 = 0; j0 < m; j0 += 4 * U) {
+    float4 v[U][NQ];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j0 + 4u * u < m) {                          // warp-uniform
+        uint32_t j = min(j0 + 4u * u + grp, m - 1u);  // clamped lanes re-read the last row (same lines)
+        const float4* p = (const float4*)(vecs + (size_t)c.cand_id[j] * c.dpad) + sub;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) v[u][t] = ld_nc_f4(p + 8 * t);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j0 + 4u * u < m) {
+        uint32_t j = j0 + 4u * u + grp;
+        float acc = group_reduce<8>(partial_dist<NQ>(v[u], qr, metric));
+        if (sub == 0 && j < m) c.cand_dist[j] = metric == 0 ? acc : 1.0f - acc;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---- LPV = 32: TMA bulk staging ring ----------------------------------------
+__device__ __forceinline__ void issue_group(WarpCtx& c, const float* __restrict__ vecs, uint32_t r, uint32_t m) {
+  uint32_t buf = r % c.NG;
+  uint32_t first = r * c.G;
+  uint32_t cnt = min(c.G, m - first);
+  if (c.lane == 0) mbar_arrive_expect_tx(&c.mbar[buf], cnt * c.vbytes);
+  __syncwarp();
+  if (c.lane < cnt) {
+    uint32_t id = c.cand_id[first + c.lane];
+    bulk_g2s(c.stage + (size_t)(buf * c.G + c.lane) * c.dpad, vecs + (size_t)id * c.dpad, c.vbytes, &c.mbar[buf]);
+  }
+}
+template <int NQ>
+__device__ __forceinline__ void eval_staged(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
+                                            uint32_t m, int metric) {
+  const uint32_t rounds = (m + c.G - 1) / c.G;
+  const uint32_t pre = min(rounds, c.NG);
+  for (uint32_t r = 0; r < pre; ++r) issue_group(c, vecs, r, m);
+#pragma unroll 1
+  for (uint32_t r = 0; r < rounds; ++r) {
+    uint32_t buf = r % c.NG;
+    mbar_wait(&c.mbar[buf], (c.phases >> buf) & 1u);
+    c.phases ^= (1u << buf);
+    uint32_t first = r * c.G;
+    uint32_t cnt = min(c.G, m - first);
+#pragma unroll 1
+    for (uint32_t v = 0; v < cnt; ++v) {
+      const float4* s4 = (const float4*)(c.stage + (size_t)(buf * c.G + v) * c.dpad) + c.lane;
+      float4 x[NQ];
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) x[t] = s4[32 * t];
+      float acc = group_reduce<32>(partial_dist<NQ>(x, qr, metric));
+      if (c.lane == 0) c.cand_dist[first + v] = metric == 0 ? acc : 1.0f - acc;
+    }
+    __syncwarp();
+    if (r + c.NG < rounds) {
+      fence_proxy_async();
+      issue_group(c, vecs, r + c.NG, m);
+    }
+  }
+  __syncwarp();
+}
+
+// cand_id[0..m) -> cand_dist[0..m): distances from the register-held query.
+template <int LPV, int NQ>
+__device__ __forceinline__ void eval_candidates(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
+                                                uint32_t m, int metric) {
+  if (LPV == 8)
+    eval_direct<NQ>(c, vecs, qr, m, metric);
+  else
+    eval_staged<NQ>(c, vecs, qr, m, metric);
+}
+
+// ---------------------------------------------------------------------------
+// Register-resident sorted key list: position i lives in lane i % 32, slot
+// i / 32; unused positions hold kMaxKey.
+// ---------------------------------------------------------------------------
+template <int KPL>
+__device__ __forceinline__ void rl_clear(uint64_t (&k)[KPL]) {
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) k[s] = kMaxKey;
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Insert `key` keeping at most `limit` entries.  Warp-uniform arguments.
+template <int KPL>
+__device__ __forceinline__ void rl_insert(uint64_t (&k)[KPL], uint64_t key, uint32_t limit, uint32_t lane) {
+  uint32_t pos = 0;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) pos += __popc(__ballot_sync(0xffffffffu, k[s] < key));
+  if (pos >= limit) return;
+#pragma unroll
+  for (int s = KPL - 1; s >= 0; --s) {
+    if ((uint32_t)(s + 1) * 32u > pos) {  // warp-uniform: slots entirely below pos are untouched
+      uint64_t up = __shfl_up_sync(0xffffffffu, k[s], 1);
+      uint64_t carry = s > 0 ? shfl64(k[s > 0 ? s - 1 : 0], 31) : 0ull;
+      uint64_t shifted = lane == 0 ? carry : up;
+      uint32_t gi = (uint32_t)s * 32u + lane;
+      uint64_t nv = gi < pos ? k[s] : (gi == pos ? key : shifted);
+      k[s] = gi >= limit ? kMaxKey : nv;
+    }
+  }
+}
+// true when some entry carries this id (only needed once the visited table overflowed)
+template <int KPL>
+__device__ __forceinline__ bool rl_contains(const uint64_t (&k)[KPL], uint32_t id) {
+  bool hit = false;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) hit |= (k[s] != kMaxKey) && key_id(k[s]) == id;
+  return __any_sync(0xffffffffu, hit);
+}
+// First unexpanded entry: returns its key (flag clear) and marks it expanded; kMaxKey if none.
+template <int KPL>
+__device__ __forceinline__ uint64_t rl_pop_unexpanded(uint64_t (&k)[KPL], uint32_t lane) {
+  uint64_t out = kMaxKey;
+  bool done = false;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    if (!done) {
+      uint32_t b = __ballot_sync(0xffffffffu, k[s] != kMaxKey && !((uint32_t)k[s] & kExpandedFlag));
+      if (b) {
+        int l = __ffs(b) - 1;
+        out = shfl64(k[s], l);
+        if ((int)lane == l) k[s] |= kExpandedFlag;
+        done = true;
+      }
+    }
+  }
+  return out;
+}
+// key at position i (warp-uniform i)
+template <int KPL>
+__device__ __forceinline__ uint64_t rl_at(const uint64_t (&k)[KPL], uint32_t i) {
+  uint64_t v = k[0];
+#pragma unroll
+  for (int s = 1; s < KPL; ++s)
+    if ((i >> 5) == (uint32_t)s) v = k[s];
+  return shfl64(v, i & 31);
+}
+template <int KPL>
+__device__ __forceinline__ uint32_t rl_count(const uint64_t (&k)[KPL]) {
+  uint32_t n = 0;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) n += __popc(__ballot_sync(0xffffffffu, k[s] != kMaxKey));
+  return n;
+}
+template <int KPL>
+__device__ __forceinline__ void rl_store(const uint64_t (&k)[KPL], uint64_t* dst, uint32_t lane) {
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) dst[s * 32 + lane] = k[s];
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory sorted key list (cold paths: brute-force select, row merge).
+// Returns the insert position, or kInvalid when rejected (duplicate id or
+// beyond the limit).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t list_insert(WarpCtx& c, uint64_t key, uint32_t limit) {
+  const uint32_t id = key_id(key);
+  uint32_t pos = 0;
+  uint32_t dup = 0;
+  for (uint32_t base = 0; base < c.cnt; base += 32) {
+    uint32_t i = base + c.lane;
+    uint64_t k = i < c.cnt ? c.keys[i] : kMaxKey;
+    pos += __popc(__ballot_sync(0xffffffffu, k < key));
+    dup |= __ballot_sync(0xffffffffu, i < c.cnt && key_id(k) == id);
+  }
+  if (dup || pos >= limit) return kInvalid;
+  const uint32_t newcnt = min(c.cnt + 1u, limit);
+  for (int base = (int)((newcnt - 1u) & ~31u); base >= (int)(pos & ~31u); base -= 32) {
+    uint32_t i = (uint32_t)base + c.lane;
+    bool in = i >= pos && i < newcnt;
+    uint64_t v = key;
+    if (in && i > pos) v = c.keys[i - 1];
+    __syncwarp();
+    if (in) c.keys[i] = v;
+  }
+  __syncwarp();
+  c.cnt = newcnt;
+  return pos;
+}
+
+struct WalkCounters {
+  uint32_t hops_upper, hops_base, evals, overflow;
+};
+
+// Adjacency row of `node` at `level` -> one id per lane (kInvalid beyond the row).
+// Branch-free (clamped index + select) so the warp never splits here.
+__device__ __forceinline__ uint32_t load_row(const GraphView& g, uint32_t node, int level, uint32_t lane) {
+  const uint32_t* row;
+  uint32_t width;
+  if (level == 0) {  // warp-uniform
+    row = g.links0 + (size_t)node * g.M0;
+    width = g.M0;
+  } else {
+    row = g.links_up + (size_t)(g.up_off[node] + (uint32_t)(level - 1)) * g.M;
+    width = g.M;
+  }
+  uint32_t v = row[min(lane, width - 1u)];
+  return lane < width ? v : kInvalid;
+}
+
+// hnswlib searchKnn's upper-layer descent: at each level move to the closest
+// neighbour until no neighbour improves.
+template <int LPV, int NQ>
+__device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], uint32_t& cur,
+                                               float& curdist, int from_level, int to_level_excl,
+                                               WalkCounters& wc) {
+  for (int level = from_level; level > to_level_excl; --level) {
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      __syncwarp();
+      uint32_t nb = load_row(g, cur, level, c.lane);
+      uint32_t mask = __ballot_sync(0xffffffffu, nb != kInvalid);
+      uint32_t m = __popc(mask);
+      wc.hops_upper++;
+      if (!m) break;
+      if (nb != kInvalid) c.cand_id[__popc(mask & lanemask_lt())] = nb;
+      __syncwarp();
+      wc.evals += m;
+      eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
+      float bd = c.lane < m ? c.cand_dist[c.lane] : INFINITY;
+      uint32_t bl = c.lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, bd, o);
+        uint32_t ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (od < bd || (od == bd && ol < bl)) bd = od, bl = ol;
+      }
+      if (bd < curdist) {
+        curdist = bd;
+        cur = c.cand_id[bl];
+        changed = true;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// hnswlib searchBaseLayer(ST): best-first beam search with an ef-bounded
+// result set.  On return k[] holds the (<= ef) closest visited nodes,
+// ascending.  `exclude` (kInvalid = none) is never admitted (used when
+// re-linking an updated node).
+template <int LPV, int NQ, int KPL, bool PREFETCH>
+__device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ],
+                                            uint64_t (&k)[KPL], uint32_t ep, float epdist, int level, uint32_t ef,
+                                            uint32_t exclude, WalkCounters& wc) {
+  hash_clear(c);
+  rl_clear<KPL>(k);
+  uint32_t ovf = 0;
+  if (c.lane == 0) {
+    hash_insert(c, ep, ovf);
+    if (exclude != kInvalid) hash_insert(c, exclude, ovf);
+  }
+  __syncwarp();
+  uint32_t cnt = 0;
+  uint32_t worst_hi = 0xFFFFFFFFu;  // ordered distance of entry ef-1 once the list is full
+  bool ovf_any = false;
+  if (ep != exclude) {
+    rl_insert<KPL>(k, make_key(epdist, ep), ef, c.lane);
+    cnt = 1;
+    if (cnt >= ef) worst_hi = key_hi(rl_at<KPL>(k, ef - 1));
+  }
+  bool pending_ep = (ep == exclude);  // an excluded entry point is still expanded once
+  for (;;) {
+    uint32_t node;
+    if (pending_ep) {
+      node = ep;
+      pending_ep = false;
+    } else {
+      uint64_t key = rl_pop_unexpanded<KPL>(k, c.lane);
+      if (key == kMaxKey) break;
+      node = key_id(key);
+    }
+    if (level == 0) wc.hops_base++; else wc.hops_upper++;
+    __syncwarp();
+    uint32_t nb = load_row(g, node, level, c.lane);
+    bool is_new = false;
+    if (nb != kInvalid) is_new = hash_insert(c, nb, ovf);
+    __syncwarp();  // hash probing diverges; reconverge before the collective section
+    uint32_t mask = __ballot_sync(0xffffffffu, is_new);
+    uint32_t m = __popc(mask);
+    if (!m) continue;
+    if (is_new) c.cand_id[__popc(mask & lanemask_lt())] = nb;
+    __syncwarp();
+    wc.evals += m;
+    eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
+    uint64_t mykey = kMaxKey;
+    if (c.lane < m) mykey = make_key(c.cand_dist[c.lane], c.cand_id[c.lane]);
+    __syncwarp();
+    ovf_any = ovf_any || __any_sync(0xffffffffu, ovf);
+    uint32_t qual = __ballot_sync(0xffffffffu, c.lane < m && key_hi(mykey) < worst_hi);
+    while (qual) {
+      int j = __ffs(qual) - 1;
+      qual &= qual - 1;
+      uint64_t kj = shfl64(mykey, j);
+      if (key_hi(kj) >= worst_hi) continue;
+      if (ovf_any && rl_contains<KPL>(k, key_id(kj))) continue;
+      rl_insert<KPL>(k, kj, ef, c.lane);
+      if (cnt < ef) cnt++;
+      if (cnt >= ef) worst_hi = key_hi(rl_at<KPL>(k, ef - 1));
+      if (PREFETCH && c.lane == 0) prefetch_l2(g.links0 + (size_t)key_id(kj) * g.M0);
+    }
+  }
+  wc.overflow |= ovf_any ? 1u : 0u;
+}
+
+}  // namespace ehb

@@ -1,0 +1,171 @@
+/* ehb200 — C ABI of the B200-native ANN backend for embeddinghub.
+ *
+ * This is the drop-in boundary: everything the reference's
+ * hnswlib-backed ANNIndex does for the k-NN hot path, as plain C entry points a
+ * cgo / ctypes / C++ caller can bind.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns an ehb_status (0 = OK); no exceptions cross the ABI;
+ *     ehb_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns every buffer; vectors are row-major contiguous fp32.
+ *   - "host" entry points take host pointers and do the H2D/D2H copies
+ *     themselves (what a Go slice / std::vector caller binds);  "_dev" entry
+ *     points take device pointers + a cudaStream_t (passed as void*) and never
+ *     synchronise, for callers that keep queries/results resident in HBM.
+ *   - results are nearest-first; rows with fewer than k hits are padded with
+ *     EHB_NO_LABEL / +inf and the true count is written to out_counts.
+ *   - searches on one index may be issued from several host threads (they are
+ *     serialised per index); mutations are exclusive.
+ *   - there is no CPU fallback: every call fails with EHB_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef EHB200_H
+#define EHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EHB_NO_LABEL UINT64_MAX
+
+typedef enum ehb_status {
+  EHB_OK = 0,
+  EHB_ERR_INVALID = 1,   /* bad argument                                      */
+  EHB_ERR_CUDA = 2,      /* CUDA runtime / launch failure, or no device        */
+  EHB_ERR_OOM = 3,       /* device or host allocation failed                   */
+  EHB_ERR_STATE = 4,     /* call not valid in the index's current state        */
+  EHB_ERR_NOT_FOUND = 5, /* unknown label                                      */
+  EHB_ERR_IO = 6         /* save / load failed                                 */
+} ehb_status;
+
+/* Distance "space".  Replaces hnswlib::L2Space (embeddinghub/embeddingstore/
+ * index.cc:12-13: squared L2, no sqrt), hnswlib::InnerProductSpace (1 - dot) and
+ * hnswlib's cosine convention (normalise on insert and on query, then IP) that
+ * the Go providers use (provider/redis.go:253, provider/pinecone.go:252). */
+typedef enum ehb_metric { EHB_L2 = 0, EHB_IP = 1, EHB_COSINE = 2 } ehb_metric;
+
+typedef enum ehb_precision { EHB_FP32 = 0, EHB_BF16 = 1 } ehb_precision;
+
+typedef struct ehb_index ehb_index; /* opaque */
+
+/* Construction parameters.  Zero-initialise, then set what you need;
+ * ehb_params_default() fills the reference's implicit hnswlib defaults
+ * (index.cc:14-15: M=16, ef_construction=200, random_seed=100; ef=10 because the
+ * reference never calls setEf; init capacity 128, index.h:21). */
+typedef struct ehb_params {
+  uint32_t dim;
+  int32_t metric;           /* ehb_metric                                      */
+  uint64_t capacity;        /* initial capacity in vectors; grows by doubling  */
+  uint32_t M;               /* 2..16 (level-0 rows hold 2*M ids)               */
+  uint32_t ef_construction;
+  uint32_t ef_search;       /* default ef of searches (hnswlib ef_)            */
+  uint64_t seed;            /* level generator seed                            */
+  int32_t device;           /* CUDA device ordinal                             */
+  uint32_t build_batch;     /* max points linked per build wave (0 = default)  */
+  uint32_t reserved[6];
+} ehb_params;
+
+typedef struct ehb_stats {
+  /* counters of the most recent graph search (hnswlib metric_hops /
+   * metric_distance_computations semantics: one hop per expanded node, one eval
+   * per unvisited neighbour + 1 for the entry point) */
+  uint64_t queries;
+  uint64_t hops_upper;
+  uint64_t hops_base;
+  uint64_t dist_evals;
+  uint64_t visited_overflow; /* queries whose visited table filled up          */
+  uint64_t algorithmic_bytes; /* hops_upper*4M + hops_base*8M + evals*4d + Q*4d */
+  /* index shape */
+  uint64_t size, capacity, upper_rows;
+  uint32_t dim, M, max_level, entry_point;
+  uint64_t device_bytes;
+} ehb_stats;
+
+const char* ehb_last_error(void);
+uint32_t ehb_abi_version(void);
+
+void ehb_params_default(ehb_params* p, uint32_t dim);
+
+/* ANNIndex::ANNIndex(dims, init_cap) — index.cc:10-18 (allocates the hnswlib
+ * arena); here: device arrays for vectors, labels, levels and adjacency. */
+int ehb_index_create(const ehb_params* p, ehb_index** out);
+int ehb_index_destroy(ehb_index* ix);
+
+/* ANNIndex::set -> hnswlib addPoint / resizeIndex — index.cc:20-37.  Insert or
+ * update-in-place (existing label).  labels == NULL assigns labels
+ * size()..size()+n-1.  Points are linked into the graph lazily by the next
+ * ehb_index_build / search (batched GPU construction replaces the reference's
+ * one-addPoint-per-row loop, version.cc:64-74). */
+int ehb_index_add(ehb_index* ix, uint64_t n, const float* vecs_host, const uint64_t* labels_host);
+int ehb_index_add_dev(ehb_index* ix, uint64_t n, const float* vecs_dev, const uint64_t* labels_host);
+int ehb_index_build(ehb_index* ix);
+
+/* hnswlib setEf (never called by the reference; named by BASELINE configs). */
+int ehb_index_set_ef(ehb_index* ix, uint32_t ef);
+int ehb_index_size(ehb_index* ix, uint64_t* out);
+
+/* Version::get of the stored vector (version.cc / storage.cc:32-36 serve this
+ * from RocksDB; the index keeps the fp32 rows resident so Get needs no KV). */
+int ehb_index_get(ehb_index* ix, uint64_t label, float* out_vec_host);
+
+/* ANNIndex::approx_nearest -> hnswlib searchKnn — index.cc:39-52, batched over
+ * nq queries.  ef == 0 uses the index default; the walk runs with max(ef, k) like
+ * searchKnn.  out_dists / out_counts may be NULL. */
+int ehb_index_search(ehb_index* ix, uint64_t nq, const float* queries_host, uint32_t k, uint32_t ef,
+                     uint64_t* out_labels_host, float* out_dists_host, uint32_t* out_counts_host);
+int ehb_index_search_dev(ehb_index* ix, uint64_t nq, const float* queries_dev, uint32_t k, uint32_t ef,
+                         uint64_t* out_labels_dev, float* out_dists_dev, uint32_t* out_counts_dev, void* stream);
+
+/* hnswlib BruteforceSearch (not used by the reference; the exact path named by
+ * the north star).  EHB_FP32 is exact with a defined total order (distance asc,
+ * insertion index asc) and canonical arithmetic (one fp32 FMA chain, k
+ * ascending) so ids are reproducible bit-for-bit.  EHB_BF16 is the tensor-core
+ * path (bf16 GEMM + fp32 re-rank of an oversampled candidate set). */
+int ehb_index_search_bruteforce(ehb_index* ix, uint64_t nq, const float* queries_host, uint32_t k, int precision,
+                                uint64_t* out_labels_host, float* out_dists_host, uint32_t* out_counts_host);
+int ehb_index_search_bruteforce_dev(ehb_index* ix, uint64_t nq, const float* queries_dev, uint32_t k, int precision,
+                                    uint64_t* out_labels_dev, float* out_dists_dev, uint32_t* out_counts_dev,
+                                    void* stream);
+
+int ehb_index_stats(ehb_index* ix, ehb_stats* out);
+
+/* Timing of the most recent search on the index's launch stream, measured with
+ * CUDA events recorded around the kernel(s): milliseconds of the graph-walk (or
+ * brute-force) kernels alone.  Synchronises on those events. */
+int ehb_index_last_kernel_ms(ehb_index* ix, float* out_ms);
+
+/* Graph exchange (hnswlib saveIndex/loadIndex are never called by the
+ * reference; persistence is a "next" row).  Layout:
+ *   levels[n] u8; links0[n][2M] u32 padded with UINT32_MAX; up_off[n] u32 = first
+ *   upper row of node i (UINT32_MAX if level 0); links_up[rows][M] u32.
+ * import replaces the whole index content (vectors are taken as stored, i.e.
+ * already normalised for cosine). */
+int ehb_index_export_graph(ehb_index* ix, float* vectors, uint64_t* labels, uint8_t* levels, uint32_t* links0,
+                           uint32_t* up_off, uint32_t* links_up, uint32_t* entry, int32_t* max_level);
+int ehb_index_import_graph(ehb_index* ix, uint64_t n, const float* vectors, const uint64_t* labels,
+                           const uint8_t* levels, const uint32_t* links0, const uint32_t* up_off,
+                           uint64_t upper_rows, const uint32_t* links_up, uint32_t entry, int32_t max_level);
+int ehb_index_save(ehb_index* ix, const char* path);
+int ehb_index_load(const char* path, int32_t device, ehb_index** out);
+
+/* Final merge of G per-shard top-k lists (each [nq][k], nearest-first, padded
+ * with EHB_NO_LABEL/+inf) gathered contiguously as [G][nq][k] — the step after
+ * the single NCCL all-gather of the range-sharded index. */
+int ehb_merge_topk_dev(uint32_t G, uint64_t nq, uint32_t k, const float* dists_dev, const uint64_t* labels_dev,
+                       float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev, int32_t device,
+                       void* stream);
+
+/* Search tuning knobs (advanced; 0 = automatic).  stage_slots: vectors staged
+ * per TMA group; stage_groups: groups in flight per warp; hash_bits: log2 of the
+ * per-warp visited table. */
+int ehb_index_set_tuning(ehb_index* ix, uint32_t stage_slots, uint32_t stage_groups, uint32_t hash_bits,
+                         uint32_t warps_per_block);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EHB200_H */
