@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""ehb200 benchmark — batched k-NN over the HNSW graph (BASELINE.json configs[1], "C2").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ehb200|reference] [--workload c2|c3s|...]
+
+A step = one pass of the hot path over one batch of Q synthetic queries.
+  value      queries/s, index and queries resident in HBM (ehb_index_search_dev), device-timed
+  e2e        queries/s through the host C-ABI entry point (ehb_index_search): pinned host
+             queries -> H2D -> walk -> D2H labels/distances/counts, all inside the timed region
+  roofline   algorithmic bytes of the walk kernel (hnswlib hop / distance-evaluation counters,
+             SURVEY.md §8d) / its CUDA-event duration, against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (hnswlib restatement) searching the SAME graph and queries on the
+             host cores of this box (rank 0, N=1 only)
+--impl reference times the oracle end to end on the host cores (its own CPU-built graph).
+
+Multi-GPU (torchrun, one rank per GPU): the index is range-sharded, every rank searches all Q
+queries over its own shard, one NCCL all-gather of the per-shard top-k, one merge kernel.
+Weak scaling: the shard size per GPU is fixed, so the whole-job aggregate is G*Q shard-level
+k-NN searches per step; `global_queries_per_s` (Q / step time) is reported next to it.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N per GPU, d, Q, k, ef, metric
+    "c2": dict(N=1_000_000, d=128, Q=1000, k=10, ef=64, metric="l2",
+               desc="HNSW N=1M d=128 Q=1k k=10 ef=64 L2 (BASELINE.json configs[1])"),
+    "c2s": dict(N=100_000, d=128, Q=1000, k=10, ef=64, metric="l2", desc="C2 at N=100k (smoke)"),
+    "c3s": dict(N=1_000_000, d=768, Q=10000, k=10, ef=128, metric="ip",
+                desc="C3 shape at N=1M: d=768 Q=10k k=10 ef=128 InnerProduct"),
+    "c3": dict(N=10_000_000, d=768, Q=10000, k=10, ef=128, metric="ip",
+               desc="HNSW N=10M d=768 Q=10k k=10 ef=128 InnerProduct (BASELINE.json configs[2])"),
+    "c5s": dict(N=1_000_000, d=128, Q=10000, k=100, ef=256, metric="cosine",
+                desc="C5 shape at N=1M per GPU: d=128 Q=10k k=100 ef=256 cosine"),
+}
+BASE_SEED, QUERY_SEED = 1234, 4321
+
+
+def gen(n, d, seed):
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, d), np.float32)
+    for i in range(0, n, 1 << 20):
+        m = min(1 << 20, n - i)
+        out[i:i + m] = rng.standard_normal((m, d), dtype=np.float32)
+    return out
+
+
+def recall_at_k(found, truth):
+    k = truth.shape[1]
+    return float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(found, truth)]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        for q in (self.Q, self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")):
+            try:
+                probe = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+                if probe.returncode != 0 or "not a valid" in (probe.stdout + probe.stderr).lower():
+                    continue
+                self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                           "--format=csv,noheader,nounits", "-lms", "20"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=self._read, daemon=True).start()
+                time.sleep(0.3)
+                return
+            except Exception:
+                self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    """The reference arm: the CPU oracle (hnswlib restatement; oracle/_ref cannot exist because the
+    hnswlib headers are not in /root/reference) with every host thread, its own CPU-built graph."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    cores = host_cores()
+    N, d, Q, k, ef = wl["N"], wl["d"], wl["Q"], wl["k"], wl["ef"]
+    # bounded sample: CPU construction is the slow part (reference: one addPoint per row)
+    budget_s = 100.0
+    base = gen(N, d, BASE_SEED)
+    q = gen(Q, d, QUERY_SEED)
+    o = orc.OracleHNSW(d, wl["metric"], N)
+    built, t0, chunk = 0, time.time(), 20000
+    while built < N and time.time() - t0 < budget_s:
+        m = min(chunk, N - built)
+        o.add(base[built:built + m], np.arange(built, built + m, dtype=np.uint64), threads=cores)
+        built += m
+    t_build = time.time() - t0
+    o.set_ef(ef)
+    for _ in range(args.warmup):
+        o.search(q, k, ef=ef, threads=cores)
+    t0 = time.time()
+    for _ in range(args.steps):
+        labels, _, _ = o.search(q, k, ef=ef, threads=cores)
+    dt = (time.time() - t0) / args.steps
+    gt, _ = orc.bruteforce(base[:built], q[:200], k, wl["metric"], threads=cores)
+    qps = Q / dt
+    sample = (f"graph built on the CPU over the first {built} of {N} base vectors in {t_build:.0f}s "
+              f"({cores} threads); each step = all {Q} queries at ef={ef}")
+    line = {
+        "impl": "reference", "metric": "k-NN queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "N": N, "N_sample": built, "d": d, "Q": Q, "k": k, "ef": ef,
+                   "metric_space": wl["metric"]},
+        "recall_at_k": recall_at_k(labels[:200], gt),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ehb(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import embeddinghub_b200 as ehb
+    from embeddinghub_b200._native import check, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; ehb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, d, Q, k, ef, metric = wl["N"], wl["d"], wl["Q"], wl["k"], wl["ef"], wl["metric"]
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- build the shard (setup, untimed) ---------------------------------------------------
+    t0 = time.time()
+    base = gen(N, d, BASE_SEED + 1000 * rank)
+    labels0 = np.arange(rank * N, (rank + 1) * N, dtype=np.uint64)  # global labels: contiguous ranges
+    ix = ehb.NativeIndex(d, metric=metric, capacity=N, device=local)
+    ix.add(base, labels0)
+    t1 = time.time()
+    ix.build()
+    t_build = time.time() - t1
+    nbatch = warmup + steps
+    qsets = [gen(Q, d, QUERY_SEED + i) for i in range(min(nbatch, 8))]  # rotated query batches
+    stream = torch.cuda.Stream()  # a real (non-default) stream: handle 0 would mean "the index's own stream"
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    dq = [torch.from_numpy(x).cuda() for x in qsets]
+    dl = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    dd = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    dc = torch.empty(Q, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    if world > 1:
+        gl = torch.empty((world, Q, k), dtype=torch.int64, device="cuda")
+        gd = torch.empty((world, Q, k), dtype=torch.float32, device="cuda")
+        ml = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+        md = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+        mc = torch.empty(Q, dtype=torch.int32, device="cuda")
+
+    def step_dev(i):
+        ix.search_dev(dq[i % len(dq)].data_ptr(), Q, k, ef, dl.data_ptr(), dd.data_ptr(), dc.data_ptr(), sptr)
+        if world > 1:
+            dist.all_gather_into_tensor(gl.view(-1), dl.view(-1))
+            dist.all_gather_into_tensor(gd.view(-1), dd.view(-1))
+            check(lib().ehb_merge_topk_dev(world, Q, k, C.c_void_p(gd.data_ptr()), C.c_void_p(gl.data_ptr()),
+                                           C.c_void_p(md.data_ptr()), C.c_void_p(ml.data_ptr()),
+                                           C.c_void_p(mc.data_ptr()), local, C.c_void_p(sptr)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing: K steps, L2 flushed between steps, device events --------------
+    for i in range(warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    kernel_ms, alg_bytes = [], []
+    barrier()
+    for i in range(steps):
+        flush.zero_()            # untimed: evicts L2 between timed iterations
+        ev[i][0].record(stream)
+        step_dev(warmup + i)
+        ev[i][1].record(stream)
+        if i < 4 or i == steps - 1:   # walk-kernel duration + counters of this launch (syncs on its events)
+            ev[i][1].synchronize()
+            kernel_ms.append(ix.last_kernel_ms())
+            alg_bytes.append(ix.stats()["algorithmic_bytes"])
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    st = ix.stats()
+    labels_dev = (ml if world > 1 else dl).cpu().numpy().view(np.uint64).copy()
+
+    # ---- end to end through the host entry point (pinned host buffers) ------------------------
+    hq = [torch.from_numpy(x).pin_memory() for x in qsets]
+    hl = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+    hd = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+    hc = torch.empty(Q, dtype=torch.int32).pin_memory()
+    L, h = lib(), ix._h
+
+    def step_e2e(i):
+        check(L.ehb_index_search(h, Q, C.c_void_p(hq[i % len(hq)].data_ptr()), k, ef, C.c_void_p(hl.data_ptr()),
+                                 C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr())))
+
+    for i in range(warmup):
+        step_e2e(i)
+    barrier()
+    t_e2e = 0.0
+    for i in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0e = time.perf_counter()
+        step_e2e(warmup + i)     # returns after the D2H of the results completed
+        t_e2e += time.perf_counter() - t0e
+    e2e_ms = t_e2e / steps * 1e3
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = t[0].item(), t[1].item()
+
+    # ---- recall vs exact ground truth (own kernels: exact fp32 brute force) ---------------------
+    qi = (warmup + steps - 1) % len(dq)
+    gt_l, gt_d, _ = ix.search_bruteforce(qsets[qi], k)
+    if world > 1:
+        tl = torch.from_numpy(gt_l.view(np.int64)).cuda()
+        td = torch.from_numpy(gt_d).cuda()
+        dist.all_gather_into_tensor(gl.view(-1), tl.view(-1))
+        dist.all_gather_into_tensor(gd.view(-1), td.view(-1))
+        check(lib().ehb_merge_topk_dev(world, Q, k, C.c_void_p(gd.data_ptr()), C.c_void_p(gl.data_ptr()),
+                                       C.c_void_p(md.data_ptr()), C.c_void_p(ml.data_ptr()),
+                                       C.c_void_p(mc.data_ptr()), local, C.c_void_p(sptr)))
+        torch.cuda.synchronize()
+        gt_l = ml.cpu().numpy().view(np.uint64)
+    rec = recall_at_k(labels_dev, gt_l)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the walk kernel ------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    k_ms = float(np.mean(kernel_ms))
+    achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "hnsw_search_kernel", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
+                "evals_per_query": st["dist_evals"] / Q, "hops_per_query": st["hops_base"] / Q}
+
+    # ---- CPU baseline: the oracle walks the SAME graph with the SAME queries (N=1 only) ---------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        cores = host_cores()
+        g = ix.export_graph()
+        o = orc.OracleHNSW(d, metric, N)
+        o.import_graph(g)
+        del g
+        qq = qsets[qi]  # the oracle normalises cosine queries itself
+        o.search(qq[:100], k, ef=ef, threads=cores)
+        reps, t0c = 0, time.time()
+        while reps < 3 or (time.time() - t0c < 8 and reps < 50):
+            cl, _, _ = o.search(qq, k, ef=ef, threads=cores)
+            reps += 1
+        cpu_qps = Q * reps / (time.time() - t0c)
+        t0c = time.time()
+        o.search(qq, k, ef=ef, threads=1)
+        cpu_1t = Q / (time.time() - t0c)
+        cpu = {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"oracle (hnswlib restatement) searching the same {N}-point graph exported from the GPU "
+                         f"build, same {Q} queries, ef={ef}; {reps} passes on {cores} threads",
+               "single_thread_queries_per_s": cpu_1t, "recall_at_k": recall_at_k(cl, gt_l),
+               "ids_equal_to_gpu_frac": float(np.mean(cl == labels_dev))}
+
+    h2d = Q * d * 4
+    d2h = Q * k * 12 + Q * 4
+    launches_per_step = 1 + (1 if metric == "cosine" else 0) + (1 if world > 1 else 0)
+    line = {
+        "metric": "k-NN queries/s", "value": world * Q / (dev_ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "N_per_gpu": N, "N_total": N * world, "d": d, "Q": Q, "k": k, "ef": ef,
+                   "metric_space": metric, "M": 16, "ef_construction": 200, "l2": "flushed between timed steps "
+                   "(256 MB write) and the index (vectors+links) is larger than L2", "parallelism":
+                   f"range-sharded x{world}, one all-gather of per-shard top-k + merge" if world > 1 else "single GPU",
+                   "build_s": round(t_build, 2), "setup_s": round(time.time() - t0, 1)},
+        "global_queries_per_s": Q / (dev_ms * 1e-3),
+        "recall_at_k": rec,
+        "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": launches_per_step * steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ehb200", choices=["ehb200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ehb(args, wl)
+
+
+if __name__ == "__main__":
+    main()
