@@ -1,0 +1,99 @@
+"""Host-side mirrors of the reference interfaces, exercised on the GPU through the C ABI."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import embeddinghub_b200 as ehb  # noqa: E402
+from embeddinghub_b200.offlinehub import Index  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_annindex_twin_runs_reference_index_test_cases():
+    exe = os.path.join(ROOT, "tests", "cpp", "index_test_cc")
+    assert os.path.exists(exe), "run make"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok ") == 4
+
+
+# embeddinghub/sdk/python/test/offlinehub_test.py — same cases, same expectations
+EMB = [("a", [1, 0]), ("b", [0, 1]), ("c", [-1, -1]), ("d", [1, 1])]
+
+
+def test_offlinehub_get_set_multiset():
+    index = Index([], 3)
+    index.set("a", [1, 2, 3])
+    assert index.get("a") == [1, 2, 3]
+    index = Index(EMB, 2)
+    assert index.get("a") == [1, 0]
+    index.set("a", [5, 5])
+    assert index.get("a") == [5, 5]
+    index.multiset({"a": [3, 3], "b": [4, 4]})
+    assert index.multiget(["a", "b", "c"]) == [[3, 3], [4, 4], [-1, -1]]
+
+
+def test_offlinehub_nn():
+    assert Index(EMB, 2).nearest_neighbor(2, key="a") == ["d", "b"]      # offlinehub_test.py:63-65
+
+
+def test_offlinehub_capacity():
+    index = Index([], 2)
+    embs = [(str(key), [1, 1]) for key in list(range(1028)) * 2]         # offlinehub_test.py:68-86
+    for i in range(0, len(embs), 4):
+        index.multiset(embs[i:i + 4])
+    assert index.size() == 1028
+    assert len(index.nearest_neighbor(5, embedding=[1, 1])) == 5
+
+
+def test_hub_nearest_neighbor_semantics():
+    hub = ehb.EmbeddingHub()
+    with pytest.raises(ehb.HubError) as e:
+        hub.nearest_neighbor("nope", 1, key="a")
+    assert e.value.code == "NOT_FOUND"
+    hub.create_space("s", 2)
+    hub.multiset("s", EMB)
+    assert hub.get("s", "c") == [-1.0, -1.0]
+    assert hub.nearest_neighbor("s", 2, key="a") == ["d", "b"]           # key mode drops the key itself
+    assert hub.nearest_neighbor("s", 1, embedding=[1, 0]) == ["a"]
+    with pytest.raises(ehb.HubError) as e:
+        hub.nearest_neighbor("s", 1, key="a", embedding=[1, 0])
+    assert e.value.code == "INVALID_ARGUMENT"
+    with pytest.raises(ehb.HubError) as e:
+        hub.nearest_neighbor("s", 1)
+    assert e.value.code == "INVALID_ARGUMENT"
+    hub.freeze_space("s")
+    with pytest.raises(ehb.HubError) as e:
+        hub.set("s", "z", [0, 0])
+    assert e.value.code == "FAILED_PRECONDITION"
+    res = hub.multi_nearest_neighbor("s", 2, keys=["a", "b"])
+    assert res[0] == ["d", "b"] and len(res[1]) == 2 and "b" not in res[1]
+
+
+def test_concurrent_searches_are_safe():
+    import threading
+
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((5000, 32), dtype=np.float32)
+    ix = ehb.NativeIndex(32, capacity=5000)
+    ix.add(base)
+    ix.build()
+    q = rng.standard_normal((64, 32), dtype=np.float32)
+    ref = ix.search(q, 5, ef=40)[0]
+    errs = []
+
+    def work():
+        try:
+            for _ in range(20):
+                assert np.array_equal(ix.search(q, 5, ef=40)[0], ref)
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work) for _ in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
