@@ -83,6 +83,7 @@ SYMBOLS = {
     "ehb_index_load": (C.c_int, [C.c_char_p, _I32, C.POINTER(_VP)]),
     "ehb_merge_topk_dev": (C.c_int, [_U32, _U64, _U32, _VP, _VP, _VP, _VP, _VP, _I32, _VP]),
     "ehb_index_set_tuning": (C.c_int, [_VP, _U32, _U32, _U32, _U32]),
+    "ehb_index_set_search_width": (C.c_int, [_VP, _U32]),
 }
 
 _LIB = None
@@ -169,6 +170,9 @@ class NativeIndex:
 
     def set_tuning(self, stage_slots=0, stage_groups=0, hash_bits=0, warps_per_block=0):
         check(lib().ehb_index_set_tuning(self._h, stage_slots, stage_groups, hash_bits, warps_per_block))
+
+    def set_search_width(self, warps_per_query):
+        check(lib().ehb_index_set_search_width(self._h, int(warps_per_query)))
 
     # -- queries ------------------------------------------------------------------
     @property

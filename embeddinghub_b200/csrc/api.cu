@@ -130,7 +130,7 @@ struct ehb_index {
   DevBuf<uint32_t> b_dst;
 
   // tuning (0 = auto)
-  uint32_t t_slots = 0, t_groups = 0, t_hash_bits = 0, t_wpb = 0;
+  uint32_t t_slots = 0, t_groups = 0, t_hash_bits = 0, t_wpb = 0, t_team = 0, t_latency = 0;
 
   ~ehb_index() {
     if (ev0) cudaEventDestroy(ev0);
@@ -163,6 +163,7 @@ struct ehb_index {
     uint32_t hb = t_hash_bits ? t_hash_bits : ceil_log2((uint64_t)ef_eff * M0 * 5 / 4 + 64);
     c.hash_bits = std::min(std::max(hb, 8u), 15u);
     c.staged = dpad > 256 ? 1 : 0;  // rows above 1 KB go through the TMA staging ring
+    c.latency_mode = 0;
     uint32_t vbytes = dpad * 4;
     uint32_t slots = std::max(4u, std::min(32u, 24576u / vbytes));
     uint32_t ng = slots >= 8 ? 4 : 2;
@@ -419,8 +420,19 @@ struct ehb_index {
     CU(stats.grow(nq * 4, 0, -1, s));
     CU(stat_sum.grow(4, 0, 0, s));
     uint32_t wpb = wpb_for(cfg, 0);
+    // Team mode: when the batch cannot fill the machine with one warp per query, T warps share a query.
+    uint32_t team = t_team;
+    if (team == 0) {  // automatic: two warps per query while every query still fits one wave (7 CTAs of 64 threads per SM)
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      team = nq <= (uint64_t)sms * 7 ? 2 : 1;
+    }
+    if (dpad > 256 || ef_eff > 256) team = 1;
     CU(cudaEventRecord(ev0, s));
-    CU(ehb::launch_search(view(), cfg, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, stats.p, wpb, s));
+    if (team >= 2)
+      CU(ehb::launch_search_team(team, view(), cfg.hash_bits, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, stats.p, s));
+    else
+      CU(ehb::launch_search(view(), cfg, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, stats.p, wpb, s));
     CU(cudaEventRecord(ev1, s));
     timed = true;
     last_nq = nq;
@@ -663,12 +675,20 @@ int ehb_index_last_kernel_ms(ehb_index* ix, float* out_ms) {
   return EHB_OK;
 }
 
+int ehb_index_set_search_width(ehb_index* ix, uint32_t warps_per_query) {
+  ENTER(ix);
+  if (warps_per_query > 4) return fail(EHB_ERR_INVALID, "warps_per_query must be 0 (auto) or 1..4");
+  ix->t_team = warps_per_query;
+  return EHB_OK;
+}
+
 int ehb_index_set_tuning(ehb_index* ix, uint32_t slots, uint32_t groups, uint32_t hash_bits, uint32_t wpb) {
   ENTER(ix);
   ix->t_slots = slots;
   ix->t_groups = groups;
   ix->t_hash_bits = hash_bits;
-  ix->t_wpb = wpb;
+  ix->t_wpb = wpb & 0xFFu;
+  ix->t_latency = (wpb >> 8) & 3u;  // bits 8..9: 0 auto, 1 off, 2 on (latency mode)
   return EHB_OK;
 }
 

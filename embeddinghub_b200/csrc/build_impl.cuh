@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) build_search_kernel(BuildGraph bg, WalkCf
   Aux a = aux_of(c);
   float4 qr[NQ];
   load_vec_regs<LPV, NQ>(qr, g.vecs + (size_t)p * g.dpad, c.lane);
-  uint64_t keys[KPL];
+  UList<KPL> ul;
   WalkCounters wc = {0, 0, 0, 0};
   const int level_p = bg.levels[p];
   const int top = g.max_level;
@@ -110,9 +110,16 @@ __global__ void __launch_bounds__(128) build_search_kernel(BuildGraph bg, WalkCf
   uint32_t* links0 = const_cast<uint32_t*>(g.links0);
   uint32_t* links_up = const_cast<uint32_t*>(g.links_up);
   for (int level = min(level_p, top); level >= 0; --level) {
-    beam_search<LPV, NQ, KPL, false>(c, g, qr, keys, cur, curdist, level, bg.efc, is_update ? p : kInvalid, wc);
-    rl_store<KPL>(keys, c.keys, c.lane);
-    c.cnt = rl_count<KPL>(keys);
+    beam_search<LPV, NQ, KPL, false>(c, g, qr, ul, cur, curdist, level, bg.efc, is_update ? p : kInvalid, wc);
+    // ascending dump into the shared-memory list the selection heuristic walks
+    c.cnt = 0;
+    for (;;) {
+      uint64_t key = ul_extract_min<KPL>(ul, c.lane);
+      if (key == kMaxKey) break;
+      if (c.lane == 0) c.keys[c.cnt] = key;
+      c.cnt++;
+    }
+    __syncwarp();
     if (c.cnt == 0) continue;
     uint32_t nsel = heuristic_select<LPV, NQ>(c, g, g.M, a);
     uint32_t width = level == 0 ? g.M0 : g.M;

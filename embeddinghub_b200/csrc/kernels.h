@@ -16,6 +16,11 @@ cudaError_t launch_search(const GraphView& g, const WalkCfg& cfg, const float* q
                           uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
                           uint32_t* stats, uint32_t warps_per_block, cudaStream_t s);
 
+// K2t — team walk (T warps per query, T in {2,4}); rows <= 1 KB and ef <= 256 only.
+cudaError_t launch_search_team(uint32_t T, const GraphView& g, uint32_t hash_bits, const float* queries, uint32_t nq,
+                               uint32_t k, uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                               uint32_t* stats, cudaStream_t s);
+
 // row-wise L2 normalisation (hnswlib cosine convention), canonical arithmetic.
 cudaError_t launch_normalize(const float* in, uint32_t in_stride, float* out, uint32_t out_stride, uint64_t n,
                              uint32_t dim, cudaStream_t s);

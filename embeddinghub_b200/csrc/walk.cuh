@@ -44,6 +44,7 @@ struct WalkCfg {
   uint32_t G;          // vectors per TMA staging group (<= 32), LPV = 32 only
   uint32_t NG;         // staging groups (ring depth, <= 8)
   uint32_t staged;     // 1 when the TMA staging ring is allocated
+  uint32_t latency_mode;  // 1: direct-load shapes keep a whole hop's vectors in flight (small batches)
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -190,10 +191,9 @@ __device__ __forceinline__ float group_reduce(float acc) {
 }
 
 // ---- LPV = 8: direct 128-bit loads, U steps (4 vectors each) in flight ------
-template <int NQ>
+template <int NQ, int U = (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2))>  // default: 64 registers of loads in flight
 __device__ __forceinline__ void eval_direct(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
                                             uint32_t m, int metric) {
-  constexpr int U = NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2);  // 64 registers of loads in flight
   const uint32_t sub = c.lane & 7u, grp = c.lane >> 3;
   __syncwarp();
 #pragma unroll 1
@@ -264,11 +264,13 @@ __device__ __forceinline__ void eval_staged(WarpCtx& c, const float* __restrict_
 }
 
 // cand_id[0..m) -> cand_dist[0..m): distances from the register-held query.
-template <int LPV, int NQ>
+// UX = 2 doubles the vectors in flight per batch on the direct-load path ("latency mode": a whole
+// 2M-neighbour hop in one round trip; needs ~64 more registers, used when the batch is small).
+template <int LPV, int NQ, int UX = 1>
 __device__ __forceinline__ void eval_candidates(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
                                                 uint32_t m, int metric) {
   if (LPV == 8)
-    eval_direct<NQ>(c, vecs, qr, m, metric);
+    eval_direct<NQ, UX * (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2))>(c, vecs, qr, m, metric);
   else
     eval_staged<NQ>(c, vecs, qr, m, metric);
 }
@@ -351,6 +353,127 @@ __device__ __forceinline__ void rl_store(const uint64_t (&k)[KPL], uint64_t* dst
 #pragma unroll
   for (int s = 0; s < KPL; ++s) dst[s * 32 + lane] = k[s];
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// Unsorted register-resident result set ("ulist"): position p = slot*32 + lane,
+// valid iff p < ef.  hnswlib keeps a max-heap (results) and a min-heap
+// (candidates); here both are one unordered array and the two heap tops are
+// found with warp reductions (redux.sync min / max on the ordered 32-bit
+// distance): insert-or-replace-worst and pop-closest-unexpanded cost ~10
+// instructions each instead of a ~70-instruction sorted insert.
+//   hi[s]: ordered distance; empty valid position = 0xFFFFFFFF; dead (p >= ef) = 0
+//   id[s]: node id | expanded flag; empty / dead = kInvalid (flag set -> never popped)
+// ---------------------------------------------------------------------------
+template <int KPL>
+struct UList {
+  uint32_t hi[KPL];
+  uint32_t id[KPL];
+};
+template <int KPL>
+__device__ __forceinline__ void ul_clear(UList<KPL>& u, uint32_t ef, uint32_t lane) {
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    u.hi[s] = ((uint32_t)s * 32u + lane) < ef ? 0xFFFFFFFFu : 0u;
+    u.id[s] = kInvalid;
+  }
+}
+// worst (largest) ordered distance over the valid positions; meaningful when the set is full
+template <int KPL>
+__device__ __forceinline__ uint32_t ul_worst(const UList<KPL>& u) {
+  uint32_t m = u.hi[0];
+#pragma unroll
+  for (int s = 1; s < KPL; ++s) m = max(m, u.hi[s]);
+  return __reduce_max_sync(0xffffffffu, m);
+}
+// Insert (hi, id) [warp-uniform]; cnt/worst_hi are maintained by the caller's copies.
+// Precondition when cnt == ef: hi < worst_hi.
+template <int KPL>
+__device__ __forceinline__ void ul_insert(UList<KPL>& u, uint32_t hi, uint32_t id, uint32_t ef, uint32_t& cnt,
+                                          uint32_t& worst_hi, uint32_t lane) {
+  bool done = false;
+  if (cnt < ef) {
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      if (!done) {
+        uint32_t b = __ballot_sync(0xffffffffu, u.id[s] == kInvalid && u.hi[s] == 0xFFFFFFFFu);
+        if (b) {
+          if ((int)lane == __ffs(b) - 1) u.hi[s] = hi, u.id[s] = id;
+          done = true;
+        }
+      }
+    }
+    cnt++;
+    if (cnt == ef) worst_hi = ul_worst<KPL>(u);
+  } else {
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      if (!done) {
+        uint32_t b = __ballot_sync(0xffffffffu, u.hi[s] == worst_hi && u.id[s] != kInvalid);
+        if (b) {
+          if ((int)lane == __ffs(b) - 1) u.hi[s] = hi, u.id[s] = id;
+          done = true;
+        }
+      }
+    }
+    worst_hi = ul_worst<KPL>(u);
+  }
+}
+// closest unexpanded entry: returns its id (flag clear) or kInvalid; mark=true sets its expanded flag
+template <int KPL>
+__device__ __forceinline__ uint32_t ul_min_unexpanded(UList<KPL>& u, bool mark, uint32_t lane) {
+  uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s)
+    if (!(u.id[s] & kExpandedFlag)) m = min(m, u.hi[s]);
+  m = __reduce_min_sync(0xffffffffu, m);
+  uint32_t node = kInvalid;
+  bool done = false;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    if (!done) {
+      uint32_t b = __ballot_sync(0xffffffffu, !(u.id[s] & kExpandedFlag) && u.hi[s] == m);
+      if (b) {
+        int l = __ffs(b) - 1;
+        node = __shfl_sync(0xffffffffu, u.id[s], l);
+        if (mark && (int)lane == l) u.id[s] |= kExpandedFlag;
+        done = true;
+      }
+    }
+  }
+  return node;
+}
+template <int KPL>
+__device__ __forceinline__ bool ul_contains(const UList<KPL>& u, uint32_t id) {
+  bool hit = false;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) hit |= u.id[s] != kInvalid && (u.id[s] & kIdMask) == id;
+  return __any_sync(0xffffffffu, hit);
+}
+// Destructive extraction in ascending order: returns the next (hi, id) or id == kInvalid when empty.
+template <int KPL>
+__device__ __forceinline__ uint64_t ul_extract_min(UList<KPL>& u, uint32_t lane) {
+  uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s)
+    if (u.id[s] != kInvalid) m = min(m, u.hi[s]);
+  m = __reduce_min_sync(0xffffffffu, m);
+  uint64_t out = kMaxKey;
+  bool done = false;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    if (!done) {
+      uint32_t b = __ballot_sync(0xffffffffu, u.id[s] != kInvalid && u.hi[s] == m);
+      if (b) {
+        int l = __ffs(b) - 1;
+        uint32_t id = __shfl_sync(0xffffffffu, u.id[s], l);
+        out = ((uint64_t)m << 32) | (id & kIdMask);
+        if ((int)lane == l) u.id[s] = kInvalid, u.hi[s] = 0xFFFFFFFFu;
+        done = true;
+      }
+    }
+  }
+  return out;
 }
 
 // ---------------------------------------------------------------------------
@@ -442,15 +565,17 @@ __device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, c
 }
 
 // hnswlib searchBaseLayer(ST): best-first beam search with an ef-bounded
-// result set.  On return k[] holds the (<= ef) closest visited nodes,
-// ascending.  `exclude` (kInvalid = none) is never admitted (used when
-// re-linking an updated node).
-template <int LPV, int NQ, int KPL, bool PREFETCH>
-__device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ],
-                                            uint64_t (&k)[KPL], uint32_t ep, float epdist, int level, uint32_t ef,
-                                            uint32_t exclude, WalkCounters& wc) {
+// result set.  On return `u` holds the (<= ef) closest visited nodes (unordered).
+// `exclude` (kInvalid = none) is never admitted (used when re-linking an updated
+// node).  The adjacency row of the likely next node (the closest unexpanded entry
+// before this hop's candidates are known) is requested ahead of the distance
+// evaluation, so its latency overlaps the vector loads.
+template <int LPV, int NQ, int KPL, bool PREFETCH, int UX = 1>
+__device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], UList<KPL>& u,
+                                            uint32_t ep, float epdist, int level, uint32_t ef, uint32_t exclude,
+                                            WalkCounters& wc) {
   hash_clear(c);
-  rl_clear<KPL>(k);
+  ul_clear<KPL>(u, ef, c.lane);
   uint32_t ovf = 0;
   if (c.lane == 0) {
     hash_insert(c, ep, ovf);
@@ -458,53 +583,48 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
   }
   __syncwarp();
   uint32_t cnt = 0;
-  uint32_t worst_hi = 0xFFFFFFFFu;  // ordered distance of entry ef-1 once the list is full
+  uint32_t worst_hi = 0xFFFFFFFFu;  // ordered distance of the worst entry once the set is full
   bool ovf_any = false;
-  if (ep != exclude) {
-    rl_insert<KPL>(k, make_key(epdist, ep), ef, c.lane);
-    cnt = 1;
-    if (cnt >= ef) worst_hi = key_hi(rl_at<KPL>(k, ef - 1));
-  }
-  bool pending_ep = (ep == exclude);  // an excluded entry point is still expanded once
+  if (ep != exclude) ul_insert<KPL>(u, f2ord(epdist), ep, ef, cnt, worst_hi, c.lane);
+  uint32_t node = ep;               // an excluded entry point is still expanded once
+  if (ep != exclude) node = ul_min_unexpanded<KPL>(u, true, c.lane);
+  uint32_t nb = load_row(g, node, level, c.lane);
   for (;;) {
-    uint32_t node;
-    if (pending_ep) {
-      node = ep;
-      pending_ep = false;
-    } else {
-      uint64_t key = rl_pop_unexpanded<KPL>(k, c.lane);
-      if (key == kMaxKey) break;
-      node = key_id(key);
-    }
     if (level == 0) wc.hops_base++; else wc.hops_upper++;
     __syncwarp();
-    uint32_t nb = load_row(g, node, level, c.lane);
+    // speculative: the row of the closest entry still unexpanded
+    const uint32_t spec = ul_min_unexpanded<KPL>(u, false, c.lane);
+    uint32_t spec_row = kInvalid;
+    if (spec != kInvalid) spec_row = load_row(g, spec & kIdMask, level, c.lane);
     bool is_new = false;
     if (nb != kInvalid) is_new = hash_insert(c, nb, ovf);
     __syncwarp();  // hash probing diverges; reconverge before the collective section
     uint32_t mask = __ballot_sync(0xffffffffu, is_new);
     uint32_t m = __popc(mask);
-    if (!m) continue;
-    if (is_new) c.cand_id[__popc(mask & lanemask_lt())] = nb;
-    __syncwarp();
-    wc.evals += m;
-    eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
-    uint64_t mykey = kMaxKey;
-    if (c.lane < m) mykey = make_key(c.cand_dist[c.lane], c.cand_id[c.lane]);
-    __syncwarp();
-    ovf_any = ovf_any || __any_sync(0xffffffffu, ovf);
-    uint32_t qual = __ballot_sync(0xffffffffu, c.lane < m && key_hi(mykey) < worst_hi);
-    while (qual) {
-      int j = __ffs(qual) - 1;
-      qual &= qual - 1;
-      uint64_t kj = shfl64(mykey, j);
-      if (key_hi(kj) >= worst_hi) continue;
-      if (ovf_any && rl_contains<KPL>(k, key_id(kj))) continue;
-      rl_insert<KPL>(k, kj, ef, c.lane);
-      if (cnt < ef) cnt++;
-      if (cnt >= ef) worst_hi = key_hi(rl_at<KPL>(k, ef - 1));
-      if (PREFETCH && c.lane == 0) prefetch_l2(g.links0 + (size_t)key_id(kj) * g.M0);
+    if (m) {
+      if (is_new) c.cand_id[__popc(mask & lanemask_lt())] = nb;
+      __syncwarp();
+      wc.evals += m;
+      eval_candidates<LPV, NQ, UX>(c, g.vecs, qr, m, g.metric);
+      uint32_t myhi = 0xFFFFFFFFu, myid = kInvalid;
+      if (c.lane < m) myhi = f2ord(c.cand_dist[c.lane]), myid = c.cand_id[c.lane];
+      __syncwarp();
+      ovf_any = ovf_any || __any_sync(0xffffffffu, ovf);
+      uint32_t qual = __ballot_sync(0xffffffffu, c.lane < m && (cnt < ef || myhi < worst_hi));
+      while (qual) {
+        int j = __ffs(qual) - 1;
+        qual &= qual - 1;
+        uint32_t hj = __shfl_sync(0xffffffffu, myhi, j);
+        uint32_t ij = __shfl_sync(0xffffffffu, myid, j);
+        if (cnt >= ef && hj >= worst_hi) continue;
+        if (ovf_any && ul_contains<KPL>(u, ij)) continue;
+        ul_insert<KPL>(u, hj, ij, ef, cnt, worst_hi, c.lane);
+        if (PREFETCH && c.lane == 0) prefetch_l2(g.links0 + (size_t)ij * g.M0);
+      }
     }
+    node = ul_min_unexpanded<KPL>(u, true, c.lane);
+    if (node == kInvalid) break;
+    nb = (node == spec) ? spec_row : load_row(g, node, level, c.lane);
   }
   wc.overflow |= ovf_any ? 1u : 0u;
 }

@@ -159,6 +159,12 @@ int ehb_merge_topk_dev(uint32_t G, uint64_t nq, uint32_t k, const float* dists_d
                        float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev, int32_t device,
                        void* stream);
 
+/* Warps cooperating on one query: 1 = the exact hnswlib expansion order (one warp
+ * per query); 2 or 4 = that many of the closest unexpanded candidates are expanded
+ * concurrently per round (recall >= the sequential walk's at the same ef; used when
+ * a batch is too small to fill the GPU with one warp per query); 0 = automatic. */
+int ehb_index_set_search_width(ehb_index* ix, uint32_t warps_per_query);
+
 /* Search tuning knobs (advanced; 0 = automatic).  stage_slots: vectors staged
  * per TMA group; stage_groups: groups in flight per warp; hash_bits: log2 of the
  * per-warp visited table. */

@@ -72,6 +72,7 @@ def test_walk_matches_oracle_on_same_graph(metric, d):
     o.add(base, threads=4)
     g = o.export_graph()
     ix = ehb.NativeIndex(d, metric=metric, capacity=n)
+    ix.set_search_width(1)          # one warp per query = hnswlib's exact expansion order
     ix.import_graph(g)
     o.metrics(reset=True)
     ol, od, oc = o.search(q, k, ef=ef)
@@ -96,11 +97,38 @@ def test_walk_reference_default_ef_and_k_gt_ef():
     o = orc.OracleHNSW(d, "l2", n)
     o.add(base)
     ix = ehb.NativeIndex(d, capacity=n)
+    ix.set_search_width(1)
     ix.import_graph(o.export_graph())
     for k in (1, 10, 25):                       # ef defaults to 10 -> walk uses max(10, k)
         ol, od, _ = o.search(q, k)
         labels, dists, _ = ix.search(q, k)
         assert np.mean(labels == ol) >= 0.99
+
+
+@pytest.mark.parametrize("metric,d,width", [("l2", 128, 2), ("ip", 64, 4), ("cosine", 32, 3), ("l2", 256, 2)])
+def test_team_walk_recall_not_below_sequential(metric, d, width):
+    """T warps per query expand T candidates per round: a superset-style exploration.  Same graph,
+    same ef: recall must not drop below the one-warp (hnswlib-order) walk, results stay sorted,
+    unique, and distances stay exact."""
+    n, nq, k = 20000, 500, 10
+    base, q = data(n, d, nq)
+    ix = ehb.NativeIndex(d, metric=metric, capacity=n)
+    ix.add(base)
+    ix.build()
+    gt, gtd, _ = ix.search_bruteforce(q, k)
+    for ef in (10, 64, 200):
+        ix.set_search_width(1)
+        l1, d1, _ = ix.search(q, k, ef=ef)
+        ev1 = ix.stats()["dist_evals"]
+        ix.set_search_width(width)
+        lt, dt, ct = ix.search(q, k, ef=ef)
+        evt = ix.stats()["dist_evals"]
+        assert np.all(ct == k) and np.all(np.diff(dt, axis=1) >= 0)
+        assert all(len(set(r.tolist())) == k for r in lt)
+        assert recall(lt, gt) >= recall(l1, gt) - 0.003, (ef, recall(lt, gt), recall(l1, gt))
+        assert evt <= 1.6 * ev1
+        hit = lt == gt
+        np.testing.assert_allclose(dt[hit], gtd[hit], rtol=RTOL, atol=1e-6)
 
 
 # ---- GPU construction ----------------------------------------------------------------

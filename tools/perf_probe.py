@@ -14,6 +14,7 @@ def main():
     Q = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
     metric = sys.argv[4] if len(sys.argv) > 4 else "l2"
     efs = [int(x) for x in (sys.argv[5].split(",") if len(sys.argv) > 5 else ["64"])]
+    width = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     k = 10
     rng = np.random.default_rng(1234)
     base = np.empty((N, d), np.float32)
@@ -24,6 +25,7 @@ def main():
     t = time.time(); ix.add(base); t_add = time.time() - t
     t = time.time(); ix.build(); t_build = time.time() - t
     print(f"N={N} d={d} add {t_add:.2f}s build {t_build:.2f}s ({N / t_build:.0f} ins/s)", flush=True)
+    ix.set_search_width(width)
     t = time.time(); gt, _, _ = ix.search_bruteforce(q, k); t_bf = time.time() - t
     print(f"bruteforce Q={Q}: {t_bf:.3f}s wall, kernel {ix.last_kernel_ms():.2f} ms", flush=True)
     for ef in efs:
