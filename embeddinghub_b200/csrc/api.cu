@@ -74,12 +74,6 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
-uint32_t ceil_log2(uint64_t v) {
-  uint32_t b = 0;
-  while ((1ull << b) < v) ++b;
-  return b;
-}
-
 }  // namespace
 
 struct ehb_index {
@@ -156,24 +150,46 @@ struct ehb_index {
     return g;
   }
 
-  // ef_eff: beam width; smem_list: capacity of the shared-memory key list (0 for plain searches)
-  ehb::WalkCfg walk_cfg(uint32_t ef_eff, uint32_t smem_list) const {
+  // ef_eff: beam width; smem_list: capacity of the shared-memory key list (0 for plain searches);
+  // jobs: warps (queries or points) of the launch; team: warps sharing one visited table.
+  ehb::WalkCfg walk_cfg(uint32_t ef_eff, uint32_t smem_list, uint64_t jobs, uint32_t team) const {
     ehb::WalkCfg c;
     c.lcap = smem_list;
-    uint32_t hb = t_hash_bits ? t_hash_bits : ceil_log2((uint64_t)ef_eff * M0 * 5 / 4 + 64);
-    c.hash_bits = std::min(std::max(hb, 8u), 15u);
     c.staged = dpad > 256 ? 1 : 0;  // rows above 1 KB go through the TMA staging ring
     c.latency_mode = 0;
     uint32_t vbytes = dpad * 4;
     uint32_t slots = std::max(4u, std::min(32u, 24576u / vbytes));
-    uint32_t ng = slots >= 8 ? 4 : 2;
-    uint32_t g = slots / ng;
+    uint32_t ng = 2;                      // two groups: math on one overlaps the copies of the other
+    uint32_t g = std::max(4u, slots / ng / 4 * 4);  // vectors per group, multiple of the 4-vector math step
     if (t_slots) g = std::min(32u, t_slots);
     if (t_groups) ng = std::min(8u, t_groups);
     c.G = std::max(1u, g);
     c.NG = std::max(1u, ng);
+    // Visited table.  A hop admits at most 2M new ids and the walk makes about ef hops.  "roomy" keeps
+    // the final load near 0.5 even on iid Gaussian data (~29 new ids per hop); but every KB of table
+    // costs occupancy, and a crowded table only costs re-evaluations (probes are bounded; duplicates
+    // are filtered against the result set): measured at d=768/ef=128, a table HALF the visited count
+    // gave +1.3 % evaluations and 1.5x the throughput of the roomy one.  So: as roomy as the
+    // occupancy target allows, never below a quarter of the worst case.
+    const uint32_t roomy = 2u * M0 * ef_eff + 64u, tight = std::max(256u, M0 * ef_eff / 4u);
+    uint32_t hs = roomy;
+    if (t_hash_bits) {
+      hs = 1u << t_hash_bits;
+    } else {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      uint64_t ctas = (jobs + team - 1) / std::max(team, 1u);
+      uint32_t want = (uint32_t)std::min<uint64_t>((ctas + sms - 1) / sms, c.staged ? 5u : 16u / team);
+      want = std::max(want, c.staged ? 4u : 4u);
+      c.hash_size = 0;
+      uint32_t fixed = ehb::warp_smem_bytes(c, dpad) * team + 1024u + (smem_list ? 256u : 0u);
+      uint32_t per_cta = (227u * 1024u) / want;
+      uint32_t avail = per_cta > fixed + 1024u ? (per_cta - fixed) / 4u : 256u;
+      hs = std::min(roomy, std::max(tight, avail));
+    }
+    c.hash_size = ehb::align_up(std::max(hs, 256u), 32);
     // stay inside the 227 KB per-block limit
-    while (ehb::warp_smem_bytes(c, dpad) + 256 > 200 * 1024 && c.hash_bits > 8) c.hash_bits--;
+    while (ehb::warp_smem_bytes(c, dpad) + 256 > 200 * 1024 && c.hash_size > 512) c.hash_size = ehb::align_up(c.hash_size / 2, 32);
     return c;
   }
   uint32_t wpb_for(const ehb::WalkCfg& c, uint32_t extra) const {
@@ -359,7 +375,8 @@ struct ehb_index {
     if (n_linked == n && pending_updates.empty()) return EHB_OK;
     const uint32_t maxb = prm.build_batch ? prm.build_batch : 16384;
     RET(ensure_build_scratch(maxb));
-    ehb::WalkCfg cfg = walk_cfg(std::max(prm.ef_construction, M), 256);
+    const uint32_t maxb0 = prm.build_batch ? prm.build_batch : 16384;
+    ehb::WalkCfg cfg = walk_cfg(std::max(prm.ef_construction, M), 256, std::min<uint64_t>(maxb0, n), 1);
     uint32_t wpb = wpb_for(cfg, 256);
     while (n_linked < n) {
       if (n_linked == 0) {
@@ -410,7 +427,17 @@ struct ehb_index {
     uint32_t ef_eff = std::max(ef_in ? ef_in : ef, k);
     if (ef_eff > ehb::kMaxEf) return fail(EHB_ERR_INVALID, "max(ef, k) must be <= 512");
     RET(build());
-    ehb::WalkCfg cfg = walk_cfg(ef_eff, 0);
+    // Warps per query: two when every query still fits one wave (7 CTAs of 64 threads per SM), i.e. when
+    // the batch is too small to fill the GPU with one warp per query (C2: 0.284 ms vs 0.409 ms); for
+    // larger batches one warp per query wins (C5 shape, Q=10k: 9.2 ms vs 10.7 ms).  Rows <= 1 KB, ef <= 256.
+    uint32_t team = t_team;
+    if (team == 0) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      team = nq <= (uint64_t)sms * 7 ? 2 : 1;
+    }
+    if (dpad > 256 || ef_eff > 256) team = 1;
+    ehb::WalkCfg cfg = walk_cfg(ef_eff, 0, nq * team, team);
     const float* q = dq;
     if (metric == EHB_COSINE) {
       CU(q_norm.grow(nq * dim, 0, -1, s));
@@ -420,17 +447,9 @@ struct ehb_index {
     CU(stats.grow(nq * 4, 0, -1, s));
     CU(stat_sum.grow(4, 0, 0, s));
     uint32_t wpb = wpb_for(cfg, 0);
-    // Team mode: when the batch cannot fill the machine with one warp per query, T warps share a query.
-    uint32_t team = t_team;
-    if (team == 0) {  // automatic: two warps per query while every query still fits one wave (7 CTAs of 64 threads per SM)
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-      team = nq <= (uint64_t)sms * 7 ? 2 : 1;
-    }
-    if (dpad > 256 || ef_eff > 256) team = 1;
     CU(cudaEventRecord(ev0, s));
     if (team >= 2)
-      CU(ehb::launch_search_team(team, view(), cfg.hash_bits, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, stats.p, s));
+      CU(ehb::launch_search_team(team, view(), cfg.hash_size, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, stats.p, s));
     else
       CU(ehb::launch_search(view(), cfg, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, stats.p, wpb, s));
     CU(cudaEventRecord(ev1, s));

@@ -285,7 +285,7 @@ cudaError_t launch_build_t(const BuildGraph& bg, const WalkCfg& cfg, const uint3
   size_t smem = (size_t)wsm * wpb;
   // the merge pass needs no visited table
   WalkCfg mcfg = cfg;
-  mcfg.hash_bits = 0;
+  mcfg.hash_size = 0;
   mcfg.lcap = 128;
   uint32_t mwsm = build_warp_smem(mcfg, bg.g.dpad);
   uint32_t mwpb = 4;

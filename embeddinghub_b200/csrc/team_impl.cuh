@@ -22,9 +22,9 @@
 
 namespace ehb {
 
-__host__ __device__ inline uint32_t team_smem_bytes(uint32_t hash_bits, uint32_t T) {
+__host__ __device__ inline uint32_t team_smem_bytes(uint32_t hash_size, uint32_t T) {
   uint32_t b = 0;
-  b += align_up(4u << hash_bits, 128);       // visited table
+  b += align_up(hash_size * 4u, 128);        // visited table
   b += 2 * align_up(T * 32u * 8u, 128);      // published pairs, double buffered
   b += 128;                                  // published counts [2][T]
   b += 2 * align_up(T * 32u * 4u, 128);      // cand_id, cand_dist
@@ -33,7 +33,7 @@ __host__ __device__ inline uint32_t team_smem_bytes(uint32_t hash_bits, uint32_t
 }
 
 template <int NQ, int KPL, int T, int U>
-__global__ void __launch_bounds__(T * 32, 7) hnsw_search_team_kernel(GraphView g, uint32_t hash_bits,
+__global__ void __launch_bounds__(T * 32, 7) hnsw_search_team_kernel(GraphView g, uint32_t hash_size,
                                                                      const float* __restrict__ queries, uint32_t nq,
                                                                      uint32_t k, uint32_t ef,
                                                                      uint64_t* __restrict__ out_labels,
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(T * 32, 7) hnsw_search_team_kernel(GraphView g
   const uint32_t q = blockIdx.x;
   const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   unsigned char* p = smem;
-  uint32_t* hash = (uint32_t*)p; p += align_up(4u << hash_bits, 128);
+  uint32_t* hash = (uint32_t*)p; p += align_up(hash_size * 4u, 128);
   uint64_t* pub = (uint64_t*)p; p += 2 * align_up(T * 32u * 8u, 128);   // [2][T][32]
   uint32_t* pubcnt = (uint32_t*)p; p += 128;                             // [2][T]
   uint32_t* cand_id = (uint32_t*)p; p += align_up(T * 32u * 4u, 128);
@@ -57,14 +57,13 @@ __global__ void __launch_bounds__(T * 32, 7) hnsw_search_team_kernel(GraphView g
   c.dpad = g.dpad;
   c.vbytes = g.dpad * 4u;
   c.hash = hash;
-  c.hmask = (1u << hash_bits) - 1u;
-  c.hshift = 32u - hash_bits;
+  c.hsize = hash_size;
   c.cand_id = cand_id + w * 32;
   c.cand_dist = cand_dist + w * 32;
   c.keys = nullptr;
   c.cnt = 0;
 
-  for (uint32_t i = tid; i < (1u << hash_bits); i += T * 32) hash[i] = kInvalid;
+  for (uint32_t i = tid; i < hash_size; i += T * 32) hash[i] = kInvalid;
   if (tid < 8) misc[tid] = 0;
   float4 qr[NQ];
   load_query_regs<8, NQ>(qr, queries + (size_t)q * g.dim, g.dim, lane);
@@ -181,14 +180,14 @@ __global__ void __launch_bounds__(T * 32, 7) hnsw_search_team_kernel(GraphView g
 }
 
 template <int NQ, int KPL, int T, int U>
-cudaError_t launch_team_t(const GraphView& g, uint32_t hash_bits, const float* queries, uint32_t nq, uint32_t k,
+cudaError_t launch_team_t(const GraphView& g, uint32_t hash_size, const float* queries, uint32_t nq, uint32_t k,
                           uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts, uint32_t* stats,
                           cudaStream_t s) {
-  size_t smem = team_smem_bytes(hash_bits, T);
+  size_t smem = team_smem_bytes(hash_size, T);
   auto kern = hnsw_search_team_kernel<NQ, KPL, T, U>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<nq, T * 32, smem, s>>>(g, hash_bits, queries, nq, k, ef, out_labels, out_dists, out_counts, stats);
+  kern<<<nq, T * 32, smem, s>>>(g, hash_size, queries, nq, k, ef, out_labels, out_dists, out_counts, stats);
   return cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ struct GraphView {
 
 struct WalkCfg {
   uint32_t lcap;       // shared-memory key list capacity (0 = none; cold paths only)
-  uint32_t hash_bits;  // log2(entries) of the visited table, 0 = none
+  uint32_t hash_size;  // entries of the visited table (multiple of 4), 0 = none
   uint32_t G;          // vectors per TMA staging group (<= 32), LPV = 32 only
   uint32_t NG;         // staging groups (ring depth, <= 8)
   uint32_t staged;     // 1 when the TMA staging ring is allocated
@@ -61,7 +61,7 @@ __host__ __device__ inline uint32_t pad_dim(uint32_t dim) {
 __host__ __device__ inline uint32_t warp_smem_bytes(const WalkCfg& c, uint32_t dpad) {
   uint32_t b = 0;
   b += align_up(c.lcap * 8u, 128);
-  b += align_up(c.hash_bits ? (4u << c.hash_bits) : 0u, 128);
+  b += align_up(c.hash_size * 4u, 128);
   b += 128;  // cand_id[32]
   b += 128;  // cand_dist[32]
   b += 128;  // mbarriers (<= 8) + spare
@@ -76,7 +76,7 @@ struct WarpCtx {
   float* cand_dist;
   uint64_t* mbar;
   float* stage;
-  uint32_t lcap, hmask, hshift, G, NG, dpad, vbytes;
+  uint32_t lcap, hsize, G, NG, dpad, vbytes;
   uint32_t phases;  // one parity bit per staging group
   uint32_t cnt;     // live entries in keys[] (shared-memory list only)
   uint32_t lane;
@@ -89,13 +89,12 @@ __device__ __forceinline__ void ctx_init(WarpCtx& c, unsigned char* base, const 
   c.NG = cfg.NG;
   c.dpad = dpad;
   c.vbytes = dpad * 4u;
-  c.hmask = cfg.hash_bits ? ((1u << cfg.hash_bits) - 1u) : 0u;
-  c.hshift = 32u - cfg.hash_bits;
+  c.hsize = cfg.hash_size;
   unsigned char* p = base;
   c.keys = (uint64_t*)p;
   p += align_up(cfg.lcap * 8u, 128);
   c.hash = (uint32_t*)p;
-  p += align_up(cfg.hash_bits ? (4u << cfg.hash_bits) : 0u, 128);
+  p += align_up(cfg.hash_size * 4u, 128);
   c.cand_id = (uint32_t*)p;
   p += 128;
   c.cand_dist = (float*)p;
@@ -114,7 +113,7 @@ __device__ __forceinline__ void ctx_init(WarpCtx& c, unsigned char* base, const 
 
 __device__ __forceinline__ void hash_clear(WarpCtx& c) {
   uint4* h4 = (uint4*)c.hash;
-  uint32_t n4 = (c.hmask + 1u) >> 2;
+  uint32_t n4 = c.hsize >> 2;
   for (uint32_t i = c.lane; i < n4; i += 32) h4[i] = make_uint4(kInvalid, kInvalid, kInvalid, kInvalid);
   __syncwarp();
 }
@@ -122,13 +121,13 @@ __device__ __forceinline__ void hash_clear(WarpCtx& c) {
 // Lane-parallel "test and set".  Returns true when id was not in the table
 // (and is now, unless the probe budget ran out -> overflow).
 __device__ __forceinline__ bool hash_insert(WarpCtx& c, uint32_t id, uint32_t& overflow) {
-  uint32_t h = (id * 0x9E3779B1u) >> c.hshift;
+  uint32_t h = __umulhi(id * 0x9E3779B1u, c.hsize);  // fast range reduction: any table size
 #pragma unroll 1
-  for (int probe = 0; probe < 32; ++probe) {
+  for (int probe = 0; probe < 8; ++probe) {  // bounded: a crowded table costs re-evaluations, never long probes
     uint32_t old = atomicCAS(&c.hash[h], kInvalid, id);
     if (old == kInvalid) return true;
     if (old == id) return false;
-    h = (h + 1u) & c.hmask;
+    h = h + 1u == c.hsize ? 0u : h + 1u;
   }
   overflow = 1;
   return true;
@@ -245,14 +244,28 @@ __device__ __forceinline__ void eval_staged(WarpCtx& c, const float* __restrict_
     c.phases ^= (1u << buf);
     uint32_t first = r * c.G;
     uint32_t cnt = min(c.G, m - first);
+    // four staged vectors per step: their shuffle reductions are independent and overlap
 #pragma unroll 1
-    for (uint32_t v = 0; v < cnt; ++v) {
-      const float4* s4 = (const float4*)(c.stage + (size_t)(buf * c.G + v) * c.dpad) + c.lane;
-      float4 x[NQ];
+    for (uint32_t v0 = 0; v0 < cnt; v0 += 4) {
+      float acc[4];
 #pragma unroll
-      for (int t = 0; t < NQ; ++t) x[t] = s4[32 * t];
-      float acc = group_reduce<32>(partial_dist<NQ>(x, qr, metric));
-      if (c.lane == 0) c.cand_dist[first + v] = metric == 0 ? acc : 1.0f - acc;
+      for (int i = 0; i < 4; ++i) {
+        uint32_t v = min(v0 + (uint32_t)i, cnt - 1u);  // clamped repeats are discarded below
+        const float4* s4 = (const float4*)(c.stage + (size_t)(buf * c.G + v) * c.dpad) + c.lane;
+        float4 x[NQ];
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) x[t] = s4[32 * t];
+        acc[i] = partial_dist<NQ>(x, qr, metric);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      }
+      if (c.lane < 4 && v0 + c.lane < cnt) {
+        float a = c.lane == 0 ? acc[0] : (c.lane == 1 ? acc[1] : (c.lane == 2 ? acc[2] : acc[3]));
+        c.cand_dist[first + v0 + c.lane] = metric == 0 ? a : 1.0f - a;
+      }
     }
     __syncwarp();
     if (r + c.NG < rounds) {
