@@ -198,25 +198,15 @@ def run_ehb(args, wl):
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     dq = [torch.from_numpy(x).cuda() for x in qsets]
-    dl = torch.empty((Q, k), dtype=torch.int64, device="cuda")
-    dd = torch.empty((Q, k), dtype=torch.float32, device="cuda")
-    dc = torch.empty(Q, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    if world > 1:
-        gl = torch.empty((world, Q, k), dtype=torch.int64, device="cuda")
-        gd = torch.empty((world, Q, k), dtype=torch.float32, device="cuda")
-        ml = torch.empty((Q, k), dtype=torch.int64, device="cuda")
-        md = torch.empty((Q, k), dtype=torch.float32, device="cuda")
-        mc = torch.empty(Q, dtype=torch.int32, device="cuda")
+    from embeddinghub_b200.sharded import ShardedSearcher
+
+    searcher = ShardedSearcher(ix, world, local)
+    last = {}
 
     def step_dev(i):
-        ix.search_dev(dq[i % len(dq)].data_ptr(), Q, k, ef, dl.data_ptr(), dd.data_ptr(), dc.data_ptr(), sptr)
-        if world > 1:
-            dist.all_gather_into_tensor(gl.view(-1), dl.view(-1))
-            dist.all_gather_into_tensor(gd.view(-1), dd.view(-1))
-            check(lib().ehb_merge_topk_dev(world, Q, k, C.c_void_p(gd.data_ptr()), C.c_void_p(gl.data_ptr()),
-                                           C.c_void_p(md.data_ptr()), C.c_void_p(ml.data_ptr()),
-                                           C.c_void_p(mc.data_ptr()), local, C.c_void_p(sptr)))
+        # per-shard walk -> (world > 1: one all-gather of the per-shard top-k -> merge kernel)
+        last["l"], last["d"], last["c"] = searcher.search_dev(dq[i % len(dq)], k, ef, sptr)
 
     def barrier():
         if world > 1:
@@ -246,7 +236,7 @@ def run_ehb(args, wl):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
     clocks = sampler.stop() if rank == 0 else None
     st = ix.stats()
-    labels_dev = (ml if world > 1 else dl).cpu().numpy().view(np.uint64).copy()
+    labels_dev = last["l"].cpu().numpy().view(np.uint64).copy()
 
     # ---- end to end through the host entry point (pinned host buffers) ------------------------
     hq = [torch.from_numpy(x).pin_memory() for x in qsets]
@@ -255,9 +245,21 @@ def run_ehb(args, wl):
     hc = torch.empty(Q, dtype=torch.int32).pin_memory()
     L, h = lib(), ix._h
 
+    dq_e2e = torch.empty((Q, d), dtype=torch.float32, device="cuda")
+
     def step_e2e(i):
-        check(L.ehb_index_search(h, Q, C.c_void_p(hq[i % len(hq)].data_ptr()), k, ef, C.c_void_p(hl.data_ptr()),
-                                 C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr())))
+        if world == 1:
+            # the public host entry point: host queries in, host labels/distances/counts out
+            check(L.ehb_index_search(h, Q, C.c_void_p(hq[i % len(hq)].data_ptr()), k, ef,
+                                     C.c_void_p(hl.data_ptr()), C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr())))
+        else:
+            # sharded: H2D of the queries, per-shard walk, all-gather, merge, D2H of the merged result
+            dq_e2e.copy_(hq[i % len(hq)], non_blocking=True)
+            ml_, md_, mc_ = searcher.search_dev(dq_e2e, k, ef, sptr)
+            hl.copy_(ml_, non_blocking=True)
+            hd.copy_(md_, non_blocking=True)
+            hc.copy_(mc_, non_blocking=True)
+            stream.synchronize()
 
     for i in range(warmup):
         step_e2e(i)
@@ -279,17 +281,9 @@ def run_ehb(args, wl):
 
     # ---- recall vs exact ground truth (own kernels: exact fp32 brute force) ---------------------
     qi = (warmup + steps - 1) % len(dq)
-    gt_l, gt_d, _ = ix.search_bruteforce(qsets[qi], k)
-    if world > 1:
-        tl = torch.from_numpy(gt_l.view(np.int64)).cuda()
-        td = torch.from_numpy(gt_d).cuda()
-        dist.all_gather_into_tensor(gl.view(-1), tl.view(-1))
-        dist.all_gather_into_tensor(gd.view(-1), td.view(-1))
-        check(lib().ehb_merge_topk_dev(world, Q, k, C.c_void_p(gd.data_ptr()), C.c_void_p(gl.data_ptr()),
-                                       C.c_void_p(md.data_ptr()), C.c_void_p(ml.data_ptr()),
-                                       C.c_void_p(mc.data_ptr()), local, C.c_void_p(sptr)))
-        torch.cuda.synchronize()
-        gt_l = ml.cpu().numpy().view(np.uint64)
+    gl_t, _, _ = searcher.search_dev(dq[qi], k, ef, sptr, bruteforce=True)   # exact, same exchange + merge
+    torch.cuda.synchronize()
+    gt_l = gl_t.cpu().numpy().view(np.uint64).copy()
     rec = recall_at_k(labels_dev, gt_l)
 
     if rank != 0:
