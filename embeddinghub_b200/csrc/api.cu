@@ -117,6 +117,9 @@ struct ehb_index {
   // brute-force scratch
   DevBuf<float> bf_dist, bf_qpad;
   DevBuf<uint64_t> bf_part, bf_run;
+  DevBuf<uint16_t> x_bf16, q_bf16;   // bf16 shadows for the tensor-core path
+  DevBuf<float> x_norm, q_norm2;
+  uint64_t bf16_rows = 0;            // rows of x_bf16 that are current (0 = stale)
 
   // build scratch
   DevBuf<uint32_t> b_edge_row, b_edge_src, b_row_cnt, b_row_fill, b_row_start, b_touched, b_seg_src, b_counters, b_ids;
@@ -318,6 +321,7 @@ struct ehb_index {
       CU(cudaStreamSynchronize(stream));  // host staging vectors go out of scope
       n = nn;
       up_rows = rows;
+      bf16_rows = 0;
     }
     return EHB_OK;
   }
@@ -470,22 +474,47 @@ struct ehb_index {
   int bruteforce_dev(uint64_t nq, const float* dq, uint32_t k, int precision, uint64_t* dl, float* dd, uint32_t* dc,
                      cudaStream_t s) {
     if (k == 0 || nq == 0) return EHB_OK;
-    if (precision != EHB_FP32) return fail(EHB_ERR_INVALID, "bf16 brute force: not available in this build");
+    if (precision != EHB_FP32 && precision != EHB_BF16) return fail(EHB_ERR_INVALID, "unknown precision");
+    const bool bf16 = precision == EHB_BF16;
+    if (bf16 && dpad % 64 != 0) return fail(EHB_ERR_INVALID, "bf16 brute force needs dim > 32 (64-wide k-blocks)");
     if (k > 2048) return fail(EHB_ERR_INVALID, "k must be <= 2048 for brute force");
+    // candidates kept by the bf16 pass: bf16 rounding perturbs each dot product by ~|q||x| 2^-9 / sqrt(d),
+    // comparable to the spacing of the best matches, so 4x (>= k + 64) of them go to the fp32 re-rank
+    const uint32_t kc = bf16 ? (uint32_t)std::min<uint64_t>(std::min<uint64_t>(2048, std::max<uint64_t>(n, 1)),
+                                                            std::max<uint64_t>(4ull * k, k + 64ull)) : k;
     ehb::BruteScratch sc;
-    sc.qb = std::min<uint64_t>(nq, 1024);
+    sc.qb = std::min<uint64_t>(nq, bf16 ? 2048 : 1024);
     sc.nc = std::min<uint64_t>(std::max<uint64_t>(n, 1), 131072);
     sc.slices = 32;
     CU(bf_dist.grow(sc.qb * sc.nc, 0, -1, s));
-    CU(bf_part.grow(sc.qb * sc.slices * k, 0, -1, s));
-    CU(bf_run.grow(nq * k, 0, -1, s));
+    CU(bf_part.grow(sc.qb * sc.slices * std::max(kc, k), 0, -1, s));
+    CU(bf_run.grow(nq * std::max(kc, k), 0, -1, s));
     CU(bf_qpad.grow(nq * dpad, 0, -1, s));
     CU(ehb::launch_pad_rows(dq, bf_qpad.p, nq, dim, dpad, metric == EHB_COSINE, s));
     sc.dist = bf_dist.p;
     sc.part_keys = bf_part.p;
     sc.run_keys = bf_run.p;
+    ehb::Bf16Ctx bctx;
+    if (bf16) {
+      // bf16 shadow of the base rows (+ squared norms), refreshed lazily after mutations
+      if (bf16_rows != n) {
+        CU(x_bf16.grow(std::max<uint64_t>(n, 1) * dpad, 0, -1, s));
+        CU(x_norm.grow(std::max<uint64_t>(n, 1), 0, -1, s));
+        CU(ehb::launch_to_bf16(vecs.p, dpad, x_bf16.p, x_norm.p, n, dpad, s));
+        bf16_rows = n;
+      }
+      CU(q_bf16.grow(nq * dpad, 0, -1, s));
+      CU(q_norm2.grow(nq, 0, -1, s));
+      CU(ehb::launch_to_bf16(bf_qpad.p, dpad, q_bf16.p, q_norm2.p, nq, dpad, s));
+      bctx.q_bf16 = q_bf16.p;
+      bctx.x_bf16 = x_bf16.p;
+      bctx.qnorm = q_norm2.p;
+      bctx.xnorm = x_norm.p;
+      bctx.kc = kc;
+    }
     CU(cudaEventRecord(ev0, s));
-    CU(ehb::launch_bruteforce_exact(vecs.p, dpad, dim, n, labels.p, metric, bf_qpad.p, nq, k, sc, dl, dd, dc, s));
+    CU(ehb::launch_bruteforce(vecs.p, dpad, dim, n, labels.p, metric == EHB_L2 ? 0 : 1, bf_qpad.p, nq, k, sc,
+                              bf16 ? &bctx : nullptr, dl, dd, dc, s));
     CU(cudaEventRecord(ev1, s));
     timed = true;
     last_nq = 0;
@@ -779,6 +808,7 @@ int ehb_index_import_graph(ehb_index* ix, uint64_t n, const float* vectors, cons
   if (!ix->identity_labels)
     for (uint64_t i = 0; i < n; ++i) ix->lookup[labels[i]] = (uint32_t)i;
   ix->n = ix->n_linked = n;
+  ix->bf16_rows = 0;
   ix->up_rows = upper_rows;
   ix->entry = entry;
   ix->max_level = n ? max_level : -1;

@@ -169,9 +169,20 @@ cudaError_t launch_bruteforce_exact(const float* vecs, uint32_t dpad, uint32_t d
                                     int metric, const float* qpad /*[nq][dpad]*/, uint64_t nq, uint32_t k,
                                     BruteScratch& sc, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
                                     cudaStream_t s) {
-  (void)dim;
+  return launch_bruteforce(vecs, dpad, dim, n, labels, metric, qpad, nq, k, sc, nullptr, out_labels, out_dists,
+                           out_counts, s);
+}
+
+// Shared driver of the exact path (bf == nullptr: fp32 distance tiles, keys are final) and of the
+// tensor-core path (bf != nullptr: bf16 GEMM tiles select bf->kc >= k candidates per query, then an
+// fp32 re-rank with the canonical arithmetic picks the k results).
+cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, uint64_t n, const uint64_t* labels,
+                              int metric, const float* qpad, uint64_t nq, uint32_t k, BruteScratch& sc,
+                              const Bf16Ctx* bf, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                              cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
-  const uint32_t kpad = align_up(k, 32);
+  const uint32_t ksel = bf ? bf->kc : k;
+  const uint32_t kpad = align_up(ksel, 32);
   const uint32_t wpb = 4;
   size_t smem = (size_t)wpb * kpad * 8;
   cudaError_t e;
@@ -182,27 +193,36 @@ cudaError_t launch_bruteforce_exact(const float* vecs, uint32_t dpad, uint32_t d
     if (e != cudaSuccess) return e;
   }
   {
-    uint64_t tot = nq * k;
+    uint64_t tot = nq * ksel;
     bf_fill_keys_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(sc.run_keys, tot);
   }
   for (uint64_t q0 = 0; q0 < nq; q0 += sc.qb) {
     uint64_t qn = sc.qb < nq - q0 ? sc.qb : nq - q0;
     for (uint64_t n0 = 0; n0 < n; n0 += sc.nc) {
       uint64_t nn = sc.nc < n - n0 ? sc.nc : n - n0;
-      dim3 grid((unsigned)((nn + TN - 1) / TN), (unsigned)((qn + TQ - 1) / TQ));
-      if (metric == 0)
-        bf_dist_kernel<0><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
-      else
-        bf_dist_kernel<1><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
+      if (bf) {
+        e = launch_bf16_dist_tile(bf->q_bf16, nq, bf->x_bf16, n, dpad, metric, bf->qnorm, bf->xnorm, q0, qn, n0, nn,
+                                  sc.dist, sc.nc, s);
+        if (e != cudaSuccess) return e;
+      } else {
+        dim3 grid((unsigned)((nn + TN - 1) / TN), (unsigned)((qn + TQ - 1) / TQ));
+        if (metric == 0)
+          bf_dist_kernel<0><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
+        else
+          bf_dist_kernel<1><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
+      }
       uint64_t want_sl = nn / 1024 ? nn / 1024 : 1;
       uint32_t slices = (uint32_t)(want_sl < sc.slices ? want_sl : sc.slices);
       uint64_t jobs = qn * slices;
-      bf_select_kernel<<<(unsigned)((jobs + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.dist, sc.nc, nn, n0, qn, slices, k,
-                                                                                 sc.part_keys);
+      bf_select_kernel<<<(unsigned)((jobs + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.dist, sc.nc, nn, n0, qn, slices,
+                                                                                 ksel, sc.part_keys);
       bf_merge_kernel<<<(unsigned)((qn + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.run_keys, sc.part_keys, q0, qn,
-                                                                              slices, k);
+                                                                              slices, ksel);
     }
   }
+  if (bf)
+    return launch_rerank(sc.run_keys, ksel, qpad, vecs, dpad, dim, metric, labels, nq, k, out_labels, out_dists,
+                         out_counts, s);
   bf_finalize_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(sc.run_keys, labels, nq, k, out_labels, out_dists,
                                                             out_counts);
   return cudaGetLastError();

@@ -41,6 +41,27 @@ cudaError_t launch_bruteforce_exact(const float* vecs, uint32_t dpad, uint32_t d
                                     BruteScratch& sc, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
                                     cudaStream_t s);
 
+// K3 — bf16 tensor-core (tcgen05) distance tiles + fp32 re-rank.
+struct Bf16Ctx {
+  const void* q_bf16;   // [nq][dpad] bf16
+  const void* x_bf16;   // [n][dpad] bf16
+  const float* qnorm;   // [nq] squared norms of the rounded queries (L2 only)
+  const float* xnorm;   // [n]
+  uint32_t kc;          // candidates kept per query before the fp32 re-rank (>= k)
+};
+cudaError_t launch_to_bf16(const float* in, uint32_t in_stride, void* out_bf16, float* norms, uint64_t n, uint32_t dpad,
+                           cudaStream_t s);
+cudaError_t launch_bf16_dist_tile(const void* q_bf16, uint64_t q_rows, const void* x_bf16, uint64_t x_rows,
+                                  uint32_t dpad, int metric, const float* qnorm, const float* xnorm, uint64_t q0,
+                                  uint64_t qn, uint64_t n0, uint64_t nn, float* dist, uint64_t ldd, cudaStream_t s);
+cudaError_t launch_rerank(const uint64_t* cand, uint32_t kc, const float* qpad, const float* vecs, uint32_t dpad,
+                          uint32_t dim, int metric, const uint64_t* labels, uint64_t nq, uint32_t k,
+                          uint64_t* out_labels, float* out_dists, uint32_t* out_counts, cudaStream_t s);
+cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, uint64_t n, const uint64_t* labels,
+                              int metric, const float* qpad, uint64_t nq, uint32_t k, BruteScratch& sc,
+                              const Bf16Ctx* bf, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
+                              cudaStream_t s);
+
 // K4 — merge of G sorted (dist,label) lists per query.
 cudaError_t launch_merge_topk(uint32_t G, uint64_t nq, uint32_t k, const float* dists, const uint64_t* labels,
                               float* out_dists, uint64_t* out_labels, uint32_t* out_counts, cudaStream_t s);

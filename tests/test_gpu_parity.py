@@ -290,3 +290,31 @@ def test_merge_topk_dev():
     assert np.array_equal(od.cpu().numpy(), np.take_along_axis(flat_d, order, 1))
     assert np.array_equal(ol.cpu().numpy().view(np.uint64), np.take_along_axis(flat_l, order, 1))
     assert np.all(oc.cpu().numpy() == k)
+
+
+# ---- bf16 tensor-core brute force (tcgen05 GEMM + fp32 re-rank) ---------------------------------------
+@pytest.mark.parametrize("metric,d,n,nq,k", [("ip", 128, 20000, 300, 10), ("l2", 64, 5000, 130, 20),
+                                             ("cosine", 768, 3000, 70, 5), ("ip", 100, 777, 5, 100),
+                                             ("l2", 256, 140000, 257, 10)])
+def test_bf16_bruteforce_matches_exact(metric, d, n, nq, k):
+    """The bf16 GEMM only nominates 4k (>= k+64) candidates; the fp32 re-rank uses the canonical arithmetic,
+    so every returned distance is bit-identical to the exact path's and the ids agree except where bf16
+    rounding pushed a true neighbour out of the candidate set (random Gaussian data: essentially never)."""
+    from embeddinghub_b200._native import BF16
+
+    base, q = data(n, d, nq)
+    ix = ehb.NativeIndex(d, metric=metric, capacity=n)
+    ix.add(base)
+    el, ed, ec = ix.search_bruteforce(q, k)
+    bl, bd, bc = ix.search_bruteforce(q, k, precision=BF16)
+    assert np.array_equal(ec, bc)
+    assert recall(bl, el) >= 0.995
+    same = bl == el
+    assert same.mean() >= 0.99
+    assert np.array_equal(bd[same].view(np.uint32), ed[same].view(np.uint32))
+    assert np.all(np.diff(bd, axis=1) >= 0)
+    # mutation invalidates the bf16 shadow copy
+    ix.add(q[:3] * 1.0, np.arange(3, dtype=np.uint64))
+    el2, _, _ = ix.search_bruteforce(q[:3], 1)
+    bl2, _, _ = ix.search_bruteforce(q[:3], 1, precision=BF16)
+    assert np.array_equal(el2, bl2) and el2[:, 0].tolist() == [0, 1, 2]
