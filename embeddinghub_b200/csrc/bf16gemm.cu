@@ -159,12 +159,20 @@ __global__ void __launch_bounds__(192, 1)
       uint64_t ncol = (uint64_t)tile_n * GN + c0;  // relative to n0
       if (qrow < qn) {
         float* out = dist + qrow * ldd + ncol;
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (ncol + j < nn) {
-            float dot = __uint_as_float(r[j]);
-            out[j] = metric == 0 ? fmaxf(qn2 + xnorm[n0 + ncol + j] - 2.0f * dot, 0.f) : 1.0f - dot;
-          }
+          float dot = __uint_as_float(r[j]);
+          float xn = (metric == 0 && ncol + j < nn) ? xnorm[n0 + ncol + j] : 0.f;
+          v[j] = metric == 0 ? fmaxf(qn2 + xn - 2.0f * dot, 0.f) : 1.0f - dot;
+        }
+        if (ncol + 32 <= nn && (ldd & 3u) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *(float4*)(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ncol + j < nn) out[j] = v[j];
         }
       }
     }
@@ -254,31 +262,41 @@ __global__ void rerank_kernel(const uint64_t* __restrict__ cand, uint32_t kc, co
                               const uint64_t* __restrict__ labels, uint64_t nq, uint32_t k,
                               uint64_t* __restrict__ out_labels, float* __restrict__ out_dists,
                               uint32_t* __restrict__ out_counts) {
-  extern __shared__ uint64_t skeys[];  // [wpb][kc]
-  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t q = (uint64_t)blockIdx.x * (blockDim.x >> 5) + w;
+  extern __shared__ uint64_t skeys[];  // [wpb][kc] keys, then [wpb][32][33] row tile, [wpb][32] query segment
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const uint64_t q = (uint64_t)blockIdx.x * wpb + w;
   if (q >= nq) return;
   uint64_t* keys = skeys + (size_t)w * kc;
+  float* tile = (float*)(skeys + (size_t)wpb * kc) + (size_t)w * (32 * 33 + 32);
+  float* qseg = tile + 32 * 33;
   const float* qv = qpad + q * dpad;
-  for (uint32_t c = lane; c < kc; c += 32) {
-    uint64_t ck = cand[q * kc + c];
-    uint64_t key = kMaxKey;
-    if (ck != kMaxKey) {
-      uint32_t idx = (uint32_t)ck;
-      const float* x = vecs + (size_t)idx * dpad;
-      float acc = 0.f;
+  // 32 candidates at a time: rows are staged 32 floats per row per step with coalesced loads, then every
+  // lane advances the canonical (k ascending, single accumulator) chain of ITS candidate by 32 terms
+  for (uint32_t c0 = 0; c0 < kc; c0 += 32) {
+    uint32_t c = c0 + lane;
+    uint64_t ck = c < kc ? cand[q * kc + c] : kMaxKey;
+    uint32_t idx = ck != kMaxKey ? (uint32_t)ck : 0u;
+    float acc = 0.f;
+    for (uint32_t s0 = 0; s0 < dim; s0 += 32) {
+      __syncwarp();
+#pragma unroll 8
+      for (uint32_t r = 0; r < 32; ++r) {
+        uint32_t ridx = __shfl_sync(0xffffffffu, idx, r);
+        tile[r * 33 + lane] = s0 + lane < dim ? vecs[(size_t)ridx * dpad + s0 + lane] : 0.f;
+      }
+      qseg[lane] = s0 + lane < dim ? qv[s0 + lane] : 0.f;
+      __syncwarp();
+      const uint32_t lim = min(32u, dim - s0);
       if (metric == 0) {
-        for (uint32_t i = 0; i < dim; ++i) {
-          float t = qv[i] - x[i];
+        for (uint32_t i = 0; i < lim; ++i) {
+          float t = qseg[i] - tile[lane * 33 + i];
           acc = fmaf(t, t, acc);
         }
       } else {
-        for (uint32_t i = 0; i < dim; ++i) acc = fmaf(qv[i], x[i], acc);
-        acc = 1.0f - acc;
+        for (uint32_t i = 0; i < lim; ++i) acc = fmaf(qseg[i], tile[lane * 33 + i], acc);
       }
-      key = make_key(acc, idx);
     }
-    keys[c] = key;
+    if (c < kc) keys[c] = ck != kMaxKey ? make_key(metric == 0 ? acc : 1.0f - acc, idx) : kMaxKey;
   }
   __syncwarp();
   uint32_t found = 0;
@@ -314,7 +332,7 @@ cudaError_t launch_rerank(const uint64_t* cand, uint32_t kc, const float* qpad, 
                           uint64_t* out_labels, float* out_dists, uint32_t* out_counts, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint32_t wpb = 4;
-  size_t smem = (size_t)wpb * kc * 8;
+  size_t smem = (size_t)wpb * kc * 8 + (size_t)wpb * (32 * 33 + 32) * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -70,8 +70,11 @@ __global__ void __launch_bounds__(256) bf_dist_kernel(const float* __restrict__ 
 }
 
 // One warp per (query, slice): sorted top-k of its slice of the distance row.
+// Keys that cannot beat the query's running k-th best (run_keys, from the chunks already merged) are
+// dropped before they cost an insert.
 __global__ void bf_select_kernel(const float* __restrict__ dist, uint64_t nc, uint64_t nn, uint64_t n0, uint64_t qn,
-                                 uint32_t slices, uint32_t k, uint64_t* __restrict__ part_keys) {
+                                 uint32_t slices, uint32_t k, uint64_t* __restrict__ part_keys,
+                                 const uint64_t* __restrict__ run_keys, uint64_t q0) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const uint64_t job = (uint64_t)blockIdx.x * wpb + w;
@@ -85,12 +88,13 @@ __global__ void bf_select_kernel(const float* __restrict__ dist, uint64_t nc, ui
   const uint64_t per = (nn + slices - 1) / slices;
   const uint64_t lo = (uint64_t)sl * per, hi = min(nn, lo + per);
   const float* row = dist + q * nc;
+  const uint64_t thr = run_keys[(q0 + q) * k + (k - 1)];  // kMaxKey until k results exist
   for (uint64_t i0 = lo; i0 < hi; i0 += 32) {
     uint64_t i = i0 + c.lane;
     uint64_t key = kMaxKey;
     if (i < hi) key = make_key(row[i], (uint32_t)(n0 + i));
     uint32_t worst_hi = c.cnt >= k ? key_hi(c.keys[k - 1]) : 0xFFFFFFFFu;
-    uint32_t qual = __ballot_sync(0xffffffffu, i < hi && (c.cnt < k || key_hi(key) < worst_hi));
+    uint32_t qual = __ballot_sync(0xffffffffu, i < hi && key < thr && (c.cnt < k || key_hi(key) < worst_hi));
     while (qual) {
       int j = __ffs(qual) - 1;
       qual &= qual - 1;
@@ -211,11 +215,15 @@ cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, ui
         else
           bf_dist_kernel<1><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
       }
-      uint64_t want_sl = nn / 1024 ? nn / 1024 : 1;
+      // one warp per (query, slice): as few slices as still fill the machine (~4096 warps) — every slice
+      // sorts its own top-k from scratch, so slices multiply the insert work
+      uint64_t want_sl = (4096 + qn - 1) / qn;
+      if (want_sl > nn / 1024) want_sl = nn / 1024 ? nn / 1024 : 1;
       uint32_t slices = (uint32_t)(want_sl < sc.slices ? want_sl : sc.slices);
+      if (slices == 0) slices = 1;
       uint64_t jobs = qn * slices;
       bf_select_kernel<<<(unsigned)((jobs + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.dist, sc.nc, nn, n0, qn, slices,
-                                                                                 ksel, sc.part_keys);
+                                                                                 ksel, sc.part_keys, sc.run_keys, q0);
       bf_merge_kernel<<<(unsigned)((qn + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.run_keys, sc.part_keys, q0, qn,
                                                                               slices, ksel);
     }
