@@ -43,6 +43,12 @@ WORKLOADS = {
                desc="HNSW N=10M d=768 Q=10k k=10 ef=128 InnerProduct (BASELINE.json configs[2])"),
     "c5s": dict(N=1_000_000, d=128, Q=10000, k=100, ef=256, metric="cosine",
                 desc="C5 shape at N=1M per GPU: d=128 Q=10k k=100 ef=256 cosine"),
+    # brute force on the bf16 tensor-core path (tcgen05 GEMM + fp32 re-rank); recall is measured against the
+    # exact fp32 path
+    "c4s": dict(N=1_000_000, d=768, Q=4096, k=100, ef=0, metric="ip", brute="bf16",
+                desc="brute force N=1M d=768 Q=4096 k=100 bf16 tensor-core path (C4 shape at N=1M)"),
+    "c4": dict(N=10_000_000, d=768, Q=4096, k=100, ef=0, metric="ip", brute="bf16",
+               desc="brute-force N=10M d=768 Q=4096 k=100 bf16 tensor-core GEMM path (BASELINE.json configs[3])"),
 }
 BASE_SEED, QUERY_SEED = 1234, 4321
 
@@ -181,6 +187,7 @@ def run_ehb(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, d, Q, k, ef, metric = wl["N"], wl["d"], wl["Q"], wl["k"], wl["ef"], wl["metric"]
+    brute = bool(wl.get("brute"))
     steps, warmup = args.steps, max(args.warmup, 3)
 
     # ---- build the shard (setup, untimed) ---------------------------------------------------
@@ -190,7 +197,8 @@ def run_ehb(args, wl):
     ix = ehb.NativeIndex(d, metric=metric, capacity=N, device=local)
     ix.add(base, labels0)
     t1 = time.time()
-    ix.build()
+    if not brute:
+        ix.build()
     t_build = time.time() - t1
     nbatch = warmup + steps
     qsets = [gen(Q, d, QUERY_SEED + i) for i in range(min(nbatch, 8))]  # rotated query batches
@@ -206,7 +214,8 @@ def run_ehb(args, wl):
 
     def step_dev(i):
         # per-shard walk -> (world > 1: one all-gather of the per-shard top-k -> merge kernel)
-        last["l"], last["d"], last["c"] = searcher.search_dev(dq[i % len(dq)], k, ef, sptr)
+        last["l"], last["d"], last["c"] = searcher.search_dev(dq[i % len(dq)], k, ef, sptr, bruteforce=brute,
+                                                              precision=1 if brute else 0)
 
     def barrier():
         if world > 1:
@@ -228,10 +237,10 @@ def run_ehb(args, wl):
         ev[i][0].record(stream)
         step_dev(warmup + i)
         ev[i][1].record(stream)
-        if i < 4 or i == steps - 1:   # walk-kernel duration + counters of this launch (syncs on its events)
+        if i < 4 or i == steps - 1:   # kernel duration + counters of this launch (syncs on its events)
             ev[i][1].synchronize()
             kernel_ms.append(ix.last_kernel_ms())
-            alg_bytes.append(ix.stats()["algorithmic_bytes"])
+            alg_bytes.append(0 if brute else ix.stats()["algorithmic_bytes"])
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
     clocks = sampler.stop() if rank == 0 else None
@@ -248,14 +257,18 @@ def run_ehb(args, wl):
     dq_e2e = torch.empty((Q, d), dtype=torch.float32, device="cuda")
 
     def step_e2e(i):
-        if world == 1:
+        if world == 1 and brute:
+            check(L.ehb_index_search_bruteforce(h, Q, C.c_void_p(hq[i % len(hq)].data_ptr()), k, 1,
+                                                C.c_void_p(hl.data_ptr()), C.c_void_p(hd.data_ptr()),
+                                                C.c_void_p(hc.data_ptr())))
+        elif world == 1:
             # the public host entry point: host queries in, host labels/distances/counts out
             check(L.ehb_index_search(h, Q, C.c_void_p(hq[i % len(hq)].data_ptr()), k, ef,
                                      C.c_void_p(hl.data_ptr()), C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr())))
         else:
             # sharded: H2D of the queries, per-shard walk, all-gather, merge, D2H of the merged result
             dq_e2e.copy_(hq[i % len(hq)], non_blocking=True)
-            ml_, md_, mc_ = searcher.search_dev(dq_e2e, k, ef, sptr)
+            ml_, md_, mc_ = searcher.search_dev(dq_e2e, k, ef, sptr, bruteforce=brute, precision=1 if brute else 0)
             hl.copy_(ml_, non_blocking=True)
             hd.copy_(md_, non_blocking=True)
             hc.copy_(mc_, non_blocking=True)
@@ -298,19 +311,41 @@ def run_ehb(args, wl):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     k_ms = float(np.mean(kernel_ms))
-    achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "hnsw_search_kernel", "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
-                "evals_per_query": st["dist_evals"] / Q, "hops_per_query": st["hops_base"] / Q}
+    if brute:
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        flops = 2.0 * Q * N * d
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": traffic, "peak_source": "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
+                    if peaks else "fallback (B200_PROFILING.md)", "kernel": "bf16_dist_gemm_kernel + select/merge + "
+                    "fp32 re-rank (whole brute-force pipeline; the GEMM tiles are written to HBM and re-read by the "
+                    "selection — not fused yet)", "kernel_ms": k_ms, "flops_per_launch": flops}
+    else:
+        achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "hnsw_search_kernel", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
+                    "evals_per_query": st["dist_evals"] / Q, "hops_per_query": st["hops_base"] / Q}
 
     # ---- CPU baseline: the oracle walks the SAME graph with the SAME queries (N=1 only) ---------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and brute:
+        from oracle import oracle as orc
+
+        cores = host_cores()
+        ns, qs = min(N, 200_000), min(Q, 256)
+        t0c = time.time()
+        orc.bruteforce(base[:ns], qsets[qi][:qs], k, metric, threads=cores)
+        dtc = time.time() - t0c
+        cpu = {"value": qs / dtc * (ns / N), "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"oracle exact scan (hnswlib BruteforceSearch semantics) of {qs} queries over the first {ns} base "
+                         f"vectors on {cores} threads, scaled by {ns}/{N} to the full base set"}
+    elif world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
 
         cores = host_cores()
@@ -337,12 +372,15 @@ def run_ehb(args, wl):
     h2d = Q * d * 4
     d2h = Q * k * 12 + Q * 4
     launches_per_step = 1 + (1 if metric == "cosine" else 0) + (1 if world > 1 else 0)
+    if brute:  # pad + 2x to_bf16 (first step) + per (q-chunk, n-chunk): GEMM, select, merge + fill + re-rank
+        nchunks = -(-Q // 2048) * -(-N // 131072)
+        launches_per_step = 3 + 3 * nchunks + 2 + (1 if world > 1 else 0)
     line = {
         "metric": "k-NN queries/s", "value": world * Q / (dev_ms * 1e-3), "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "N_per_gpu": N, "N_total": N * world, "d": d, "Q": Q, "k": k, "ef": ef,
-                   "metric_space": metric, "M": 16, "ef_construction": 200, "l2": "flushed between timed steps "
+                   "metric_space": metric, "M": 16, "ef_construction": 200, "path": "bruteforce bf16 tcgen05 + fp32 re-rank" if brute else "graph walk", "l2": "flushed between timed steps "
                    "(256 MB write) and the index (vectors+links) is larger than L2", "parallelism":
                    f"range-sharded x{world}, one all-gather of per-shard top-k + merge" if world > 1 else "single GPU",
                    "build_s": round(t_build, 2), "setup_s": round(time.time() - t0, 1)},

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t* tmem_full = empty + GSTAGES;
   uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile_n = blockIdx.x, tile_q = blockIdx.y;
+  // query tiles vary fastest: the CTAs that share one 256-row base tile run together, so the base set is
+  // read from HBM once per chunk (ncu, base-tile-fastest order: 3.2 GB read per launch for a 0.2 GB chunk)
+  const uint32_t tile_q = blockIdx.x, tile_n = blockIdx.y;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < GSTAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
@@ -247,7 +249,7 @@ cudaError_t launch_bf16_dist_tile(const void* q_bf16, uint64_t q_rows, const voi
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((unsigned)((nn + GN - 1) / GN), (unsigned)((qn + GM - 1) / GM));
+  dim3 grid((unsigned)((qn + GM - 1) / GM), (unsigned)((nn + GN - 1) / GN));
   bf16_dist_gemm_kernel<<<grid, 192, kGemmSmem, s>>>(mq, mx, dpad / GK, metric == 0 ? 0 : 1, qnorm, xnorm, q0, qn, n0,
                                                     nn, dist, ldd);
   return cudaGetLastError();

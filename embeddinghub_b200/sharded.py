@@ -67,13 +67,13 @@ class ShardedSearcher:
                 md=t.empty((nq, k), dtype=t.float32, device=dev), mc=t.empty(nq, dtype=t.int32, device=dev))
         return self._buf[key]
 
-    def search_dev(self, q, k, ef, stream_ptr, bruteforce=False):
+    def search_dev(self, q, k, ef, stream_ptr, bruteforce=False, precision=0):
         """q: CUDA float32 tensor [nq, dim].  Returns (labels int64-viewed-u64, dists, counts) CUDA tensors
         holding the global top-k on every rank.  Nothing synchronises the host."""
         nq = q.shape[0]
         b = self._bufs(nq, k)
         if bruteforce:
-            self.ix.search_bruteforce_dev(q.data_ptr(), nq, k, 0, b["l"].data_ptr(), b["d"].data_ptr(),
+            self.ix.search_bruteforce_dev(q.data_ptr(), nq, k, precision, b["l"].data_ptr(), b["d"].data_ptr(),
                                           b["c"].data_ptr(), stream_ptr)
         else:
             self.ix.search_dev(q.data_ptr(), nq, k, ef, b["l"].data_ptr(), b["d"].data_ptr(), b["c"].data_ptr(),
