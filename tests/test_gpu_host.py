@@ -97,3 +97,48 @@ def test_concurrent_searches_are_safe():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs
+
+
+def test_grpc_server_speaks_the_reference_contract():
+    import grpc
+
+    from embeddinghub_b200 import grpc_server as gs
+
+    server, port = gs.make_server("127.0.0.1:0")
+    server.start()
+    try:
+        stub = gs.Stub(grpc.insecure_channel(f"127.0.0.1:{port}"))
+        M = gs.M
+        emb = lambda v: M["Embedding"](values=v)  # noqa: E731
+        with pytest.raises(grpc.RpcError) as e:
+            stub.NearestNeighbor(M["NearestNeighborRequest"](num=1, space="nope", key="a"))
+        assert e.value.code() == grpc.StatusCode.NOT_FOUND                       # server.cc:178
+        stub.CreateSpace(M["CreateSpaceRequest"](name="s", dims=2))
+        stub.Set(M["SetRequest"](key="a", embedding=emb([1, 0]), space="s"))
+        stub.MultiSet(iter([M["MultiSetRequest"](key=k, embedding=emb(v), space="s")
+                            for k, v in [("b", [0, 1]), ("c", [-1, -1]), ("d", [1, 1])]]))
+        assert list(stub.Get(M["GetRequest"](key="c", space="s")).embedding.values) == [-1.0, -1.0]
+        got = [list(r.embedding.values) for r in stub.MultiGet(iter([M["MultiGetRequest"](key=k, space="s") for k in "ab"]))]
+        assert got == [[1.0, 0.0], [0.0, 1.0]]
+        nn = stub.NearestNeighbor(M["NearestNeighborRequest"](num=2, space="s", key="a"))
+        assert list(nn.keys) == ["d", "b"]                                        # key mode drops the key itself
+        nn = stub.NearestNeighbor(M["NearestNeighborRequest"](num=1, space="s", embedding=emb([1, 0])))
+        assert list(nn.keys) == ["a"]
+        with pytest.raises(grpc.RpcError) as e:
+            stub.NearestNeighbor(M["NearestNeighborRequest"](num=1, space="s", key="a", embedding=emb([1, 0])))
+        assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT                 # server.cc:183-186
+        assert sorted(r.key for r in stub.Download(M["DownloadRequest"](space="s"))) == ["a", "b", "c", "d"]
+        # concurrent embedding-mode calls are coalesced into batched searches
+        import concurrent.futures as cf
+
+        with cf.ThreadPoolExecutor(16) as ex:
+            outs = list(ex.map(lambda i: list(stub.NearestNeighbor(
+                M["NearestNeighborRequest"](num=1, space="s", embedding=emb([1, 0] if i % 2 else [0, 1]))).keys),
+                range(64)))
+        assert outs == [["a"] if i % 2 else ["b"] for i in range(64)]
+        stub.FreezeSpace(M["FreezeSpaceRequest"](name="s"))
+        with pytest.raises(grpc.RpcError) as e:
+            stub.Set(M["SetRequest"](key="z", embedding=emb([0, 0]), space="s"))
+        assert e.value.code() == grpc.StatusCode.FAILED_PRECONDITION              # server.cc:124-127
+    finally:
+        server.stop(0)
