@@ -53,12 +53,19 @@ WORKLOADS = {
 BASE_SEED, QUERY_SEED = 1234, 4321
 
 
+DIST = "gaussian"   # --dist gmm: report-only secondary distribution: 1024-centre GMM, sigma 0.3
+
+
 def gen(n, d, seed):
     rng = np.random.default_rng(seed)
     out = np.empty((n, d), np.float32)
+    centres = np.random.default_rng(99).standard_normal((1024, d), dtype=np.float32) if DIST == "gmm" else None
     for i in range(0, n, 1 << 20):
         m = min(1 << 20, n - i)
         out[i:i + m] = rng.standard_normal((m, d), dtype=np.float32)
+        if centres is not None:
+            out[i:i + m] *= np.float32(0.3)
+            out[i:i + m] += centres[rng.integers(0, 1024, m)]
     return out
 
 
@@ -378,7 +385,7 @@ def run_ehb(args, wl):
     line = {
         "metric": "k-NN queries/s", "value": world * Q / (dev_ms * 1e-3), "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic" if DIST == "gaussian" else "synthetic (gmm)",
         "config": {"workload": wl["desc"], "N_per_gpu": N, "N_total": N * world, "d": d, "Q": Q, "k": k, "ef": ef,
                    "metric_space": metric, "M": 16, "ef_construction": 200, "path": "bruteforce bf16 tcgen05 + fp32 re-rank" if brute else "graph walk", "l2": "flushed between timed steps "
                    "(256 MB write) and the index (vectors+links) is larger than L2", "parallelism":
@@ -401,13 +408,18 @@ def run_ehb(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ehb200", choices=["ehb200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist", default="gaussian", choices=["gaussian", "gmm"])
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    global DIST
+    DIST = args.dist
+    wl = dict(WORKLOADS[args.workload])
+    if DIST != "gaussian":
+        wl["desc"] += " [secondary distribution: 1024-centre GMM, sigma 0.3]"
     if args.impl == "reference":
         run_reference(args, wl)
     else:

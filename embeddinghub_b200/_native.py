@@ -82,6 +82,7 @@ SYMBOLS = {
     "ehb_index_save": (C.c_int, [_VP, C.c_char_p]),
     "ehb_index_load": (C.c_int, [C.c_char_p, _I32, C.POINTER(_VP)]),
     "ehb_merge_topk_dev": (C.c_int, [_U32, _U64, _U32, _VP, _VP, _VP, _VP, _VP, _I32, _VP]),
+    "ehb_merge_topk_packed_dev": (C.c_int, [_U32, _U64, _U32, _VP, _U64, _VP, _VP, _VP, _I32, _VP]),
     "ehb_index_set_tuning": (C.c_int, [_VP, _U32, _U32, _U32, _U32]),
     "ehb_index_set_search_width": (C.c_int, [_VP, _U32]),
 }

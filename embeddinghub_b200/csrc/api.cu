@@ -894,7 +894,21 @@ int ehb_merge_topk_dev(uint32_t G, uint64_t nq, uint32_t k, const float* dists, 
   if (G == 0 || G > 32) return fail(EHB_ERR_INVALID, "G must be in 1..32");
   if (nq && k && (!dists || !labels || !out_labels)) return fail(EHB_ERR_INVALID, "null buffer");
   CU(cudaSetDevice(device));
-  CU(ehb::launch_merge_topk(G, nq, k, dists, labels, out_dists, out_labels, out_counts, (cudaStream_t)stream));
+  CU(ehb::launch_merge_topk(G, nq, k, dists, labels, nq * k * 4ull, nq * k * 8ull, out_dists, out_labels, out_counts,
+                            (cudaStream_t)stream));
+  return EHB_OK;
+}
+
+int ehb_merge_topk_packed_dev(uint32_t G, uint64_t nq, uint32_t k, const void* packed, uint64_t rank_stride_bytes,
+                              float* out_dists, uint64_t* out_labels, uint32_t* out_counts, int32_t device,
+                              void* stream) {
+  if (G == 0 || G > 32) return fail(EHB_ERR_INVALID, "G must be in 1..32");
+  if (nq && k && (!packed || !out_labels)) return fail(EHB_ERR_INVALID, "null buffer");
+  if (rank_stride_bytes < nq * k * 12ull || (rank_stride_bytes & 7u)) return fail(EHB_ERR_INVALID, "bad rank stride");
+  CU(cudaSetDevice(device));
+  const unsigned char* base = (const unsigned char*)packed;
+  CU(ehb::launch_merge_topk(G, nq, k, (const float*)(base + nq * k * 8ull), (const uint64_t*)base, rank_stride_bytes,
+                            rank_stride_bytes, out_dists, out_labels, out_counts, (cudaStream_t)stream));
   return EHB_OK;
 }
 

@@ -240,15 +240,19 @@ cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, ui
 // K4: per query, G sorted lists of (dist, label) -> global top-k.  One warp per
 // query, lane g walks list g; each step a warp arg-min on (distance, label).
 // ---------------------------------------------------------------------------
+// rank g's lists start at (bytes) dists + g * stride_d and labels + g * stride_l, so separate [G][nq][k]
+// arrays and one packed all-gather buffer [G][labels | dists] are both merged in place.
 __global__ void merge_topk_kernel(uint32_t G, uint64_t nq, uint32_t k, const float* __restrict__ dists,
-                                  const uint64_t* __restrict__ labels, float* __restrict__ out_dists,
-                                  uint64_t* __restrict__ out_labels, uint32_t* __restrict__ out_counts) {
+                                  const uint64_t* __restrict__ labels, uint64_t stride_d, uint64_t stride_l,
+                                  float* __restrict__ out_dists, uint64_t* __restrict__ out_labels,
+                                  uint32_t* __restrict__ out_counts) {
   uint64_t q = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   uint32_t lane = threadIdx.x & 31;
   if (q >= nq) return;
   uint32_t head = 0;
-  const float* dl = dists + ((uint64_t)lane * nq + q) * k;
-  const uint64_t* ll = labels + ((uint64_t)lane * nq + q) * k;
+  const uint32_t g = lane < G ? lane : 0;
+  const float* dl = (const float*)((const unsigned char*)dists + (uint64_t)g * stride_d) + q * k;
+  const uint64_t* ll = (const uint64_t*)((const unsigned char*)labels + (uint64_t)g * stride_l) + q * k;
   uint32_t found = 0;
   for (uint32_t i = 0; i < k; ++i) {
     uint32_t od = 0xFFFFFFFFu;
@@ -285,10 +289,11 @@ __global__ void merge_topk_kernel(uint32_t G, uint64_t nq, uint32_t k, const flo
 }
 
 cudaError_t launch_merge_topk(uint32_t G, uint64_t nq, uint32_t k, const float* dists, const uint64_t* labels,
-                              float* out_dists, uint64_t* out_labels, uint32_t* out_counts, cudaStream_t s) {
+                              uint64_t stride_d, uint64_t stride_l, float* out_dists, uint64_t* out_labels,
+                              uint32_t* out_counts, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
-  merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(G, nq, k, dists, labels, out_dists, out_labels,
-                                                           out_counts);
+  merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(G, nq, k, dists, labels, stride_d, stride_l, out_dists,
+                                                           out_labels, out_counts);
   return cudaGetLastError();
 }
 

@@ -64,7 +64,8 @@ cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, ui
 
 // K4 — merge of G sorted (dist,label) lists per query.
 cudaError_t launch_merge_topk(uint32_t G, uint64_t nq, uint32_t k, const float* dists, const uint64_t* labels,
-                              float* out_dists, uint64_t* out_labels, uint32_t* out_counts, cudaStream_t s);
+                              uint64_t stride_d_bytes, uint64_t stride_l_bytes, float* out_dists, uint64_t* out_labels,
+                              uint32_t* out_counts, cudaStream_t s);
 
 // K5 — batched graph construction.
 struct BuildBuffers {

@@ -31,18 +31,23 @@ def route_rows(vecs, labels, n_total, world, rank):
 
 def gather_topk(local_labels, local_dists, world, group=None):
     """The single exchange step: all ranks contribute [nq, k] (int64-viewed u64 labels, f32
-    distances) and receive [world, nq, k].  Works on CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    distances) and receive [world, nq, k] of each.  Labels and distances travel in ONE all-gather
+    (packed per rank as [labels bytes | distance bytes]).  Works on CUDA tensors (NCCL) and CPU
+    tensors (gloo)."""
     import torch
     import torch.distributed as dist
 
     nq, k = local_labels.shape
-    gl = torch.empty((world, nq, k), dtype=local_labels.dtype, device=local_labels.device)
-    gd = torch.empty((world, nq, k), dtype=local_dists.dtype, device=local_dists.device)
     if world == 1:
-        gl[0], gd[0] = local_labels, local_dists
-    else:
-        dist.all_gather_into_tensor(gl.view(-1), local_labels.contiguous().view(-1), group=group)
-        dist.all_gather_into_tensor(gd.view(-1), local_dists.contiguous().view(-1), group=group)
+        return local_labels.unsqueeze(0), local_dists.unsqueeze(0)
+    nl, nd = nq * k * 8, nq * k * 4
+    send = torch.empty(nl + nd, dtype=torch.uint8, device=local_labels.device)
+    send[:nl].view(torch.int64).copy_(local_labels.contiguous().view(-1))
+    send[nl:].view(torch.float32).copy_(local_dists.contiguous().view(-1))
+    recv = torch.empty((world, nl + nd), dtype=torch.uint8, device=local_labels.device)
+    dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+    gl = recv[:, :nl].contiguous().view(torch.int64).view(world, nq, k)
+    gd = recv[:, nl:].contiguous().view(torch.float32).view(world, nq, k)
     return gl, gd
 
 
@@ -61,15 +66,22 @@ class ShardedSearcher:
         key = (nq, k)
         if key not in self._buf:
             dev = t.device("cuda", self.device)
+            nl, nd = nq * k * 8, nq * k * 4
+            send = t.empty(nl + nd, dtype=t.uint8, device=dev)     # [labels | distances], written by the kernels
             self._buf[key] = dict(
-                l=t.empty((nq, k), dtype=t.int64, device=dev), d=t.empty((nq, k), dtype=t.float32, device=dev),
+                send=send, l=send[:nl].view(t.int64).view(nq, k), d=send[nl:].view(t.float32).view(nq, k),
+                recv=t.empty((self.world, nl + nd), dtype=t.uint8, device=dev),
                 c=t.empty(nq, dtype=t.int32, device=dev), ml=t.empty((nq, k), dtype=t.int64, device=dev),
                 md=t.empty((nq, k), dtype=t.float32, device=dev), mc=t.empty(nq, dtype=t.int32, device=dev))
         return self._buf[key]
 
     def search_dev(self, q, k, ef, stream_ptr, bruteforce=False, precision=0):
         """q: CUDA float32 tensor [nq, dim].  Returns (labels int64-viewed-u64, dists, counts) CUDA tensors
-        holding the global top-k on every rank.  Nothing synchronises the host."""
+        holding the global top-k on every rank.  Nothing synchronises the host.  The per-shard kernels write
+        straight into the packed send buffer; ONE all-gather; the merge kernel reads the gathered blocks in
+        place."""
+        import torch.distributed as dist
+
         nq = q.shape[0]
         b = self._bufs(nq, k)
         if bruteforce:
@@ -80,8 +92,9 @@ class ShardedSearcher:
                                stream_ptr)
         if self.world == 1:
             return b["l"], b["d"], b["c"]
-        gl, gd = gather_topk(b["l"], b["d"], self.world, self.group)
-        check(lib().ehb_merge_topk_dev(self.world, nq, k, C.c_void_p(gd.data_ptr()), C.c_void_p(gl.data_ptr()),
-                                       C.c_void_p(b["md"].data_ptr()), C.c_void_p(b["ml"].data_ptr()),
-                                       C.c_void_p(b["mc"].data_ptr()), self.device, C.c_void_p(stream_ptr)))
+        dist.all_gather_into_tensor(b["recv"].view(-1), b["send"], group=self.group)
+        check(lib().ehb_merge_topk_packed_dev(self.world, nq, k, C.c_void_p(b["recv"].data_ptr()),
+                                              b["recv"].shape[1], C.c_void_p(b["md"].data_ptr()),
+                                              C.c_void_p(b["ml"].data_ptr()), C.c_void_p(b["mc"].data_ptr()),
+                                              self.device, C.c_void_p(stream_ptr)))
         return b["ml"], b["md"], b["mc"]

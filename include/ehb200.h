@@ -159,6 +159,13 @@ int ehb_merge_topk_dev(uint32_t G, uint64_t nq, uint32_t k, const float* dists_d
                        float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev, int32_t device,
                        void* stream);
 
+/* Same merge over ONE packed gather buffer: rank g's block starts at packed + g * rank_stride_bytes and
+ * holds [nq*k u64 labels | nq*k f32 distances] — what a single all-gather of each rank's packed
+ * (labels, distances) result delivers, merged in place without unpacking. */
+int ehb_merge_topk_packed_dev(uint32_t G, uint64_t nq, uint32_t k, const void* packed_dev, uint64_t rank_stride_bytes,
+                              float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev, int32_t device,
+                              void* stream);
+
 /* Warps cooperating on one query: 1 = the exact hnswlib expansion order (one warp
  * per query); 2 or 4 = that many of the closest unexpanded candidates are expanded
  * concurrently per round (recall >= the sequential walk's at the same ef; used when

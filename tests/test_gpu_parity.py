@@ -318,3 +318,35 @@ def test_bf16_bruteforce_matches_exact(metric, d, n, nq, k):
     el2, _, _ = ix.search_bruteforce(q[:3], 1)
     bl2, _, _ = ix.search_bruteforce(q[:3], 1, precision=BF16)
     assert np.array_equal(el2, bl2) and el2[:, 0].tolist() == [0, 1, 2]
+
+
+def test_merge_topk_packed_dev():
+    """One packed gather buffer [G][nq*k u64 labels | nq*k f32 dists] merged in place == separate-array merge."""
+    import ctypes as C
+
+    import torch
+
+    from embeddinghub_b200._native import check, lib
+
+    G, nq, k = 3, 50, 8
+    rng = np.random.default_rng(1)
+    d = np.sort(rng.standard_normal((G, nq, k)).astype(np.float32), axis=2)
+    lab = rng.permutation(G * nq * k).astype(np.uint64).reshape(G, nq, k)
+    nl, nd = nq * k * 8, nq * k * 4
+    packed = np.zeros((G, nl + nd), np.uint8)
+    for g in range(G):
+        packed[g, :nl] = lab[g].reshape(-1).view(np.uint8)
+        packed[g, nl:] = d[g].reshape(-1).view(np.uint8)
+    tp = torch.from_numpy(packed).cuda()
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    ol = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    oc = torch.empty(nq, dtype=torch.int32, device="cuda")
+    check(lib().ehb_merge_topk_packed_dev(G, nq, k, C.c_void_p(tp.data_ptr()), nl + nd, C.c_void_p(od.data_ptr()),
+                                          C.c_void_p(ol.data_ptr()), C.c_void_p(oc.data_ptr()), 0,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    flat_d = np.transpose(d, (1, 0, 2)).reshape(nq, -1)
+    flat_l = np.transpose(lab, (1, 0, 2)).reshape(nq, -1)
+    order = np.argsort(flat_d, axis=1, kind="stable")[:, :k]
+    assert np.array_equal(od.cpu().numpy(), np.take_along_axis(flat_d, order, 1))
+    assert np.array_equal(ol.cpu().numpy().view(np.uint64), np.take_along_axis(flat_l, order, 1))
