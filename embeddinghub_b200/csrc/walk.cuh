@@ -619,6 +619,13 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       __syncwarp();
       wc.evals += m;
       eval_candidates<LPV, NQ, UX>(c, g.vecs, qr, m, g.metric);
+      // the speculative row has arrived by now: pull its neighbours' vectors towards L2 while this hop's
+      // candidates are inserted (rows <= 1 KB only; a wrong guess costs bandwidth, not correctness)
+      if (PREFETCH && LPV == 8 && spec_row != kInvalid) {
+        const char* pv = (const char*)(g.vecs + (size_t)spec_row * g.dpad);
+#pragma unroll
+        for (int b = 0; b < NQ * 8 * 16; b += 128) prefetch_l2(pv + b);
+      }
       uint32_t myhi = 0xFFFFFFFFu, myid = kInvalid;
       if (c.lane < m) myhi = f2ord(c.cand_dist[c.lane]), myid = c.cand_id[c.lane];
       __syncwarp();
