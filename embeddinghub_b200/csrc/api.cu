@@ -124,10 +124,9 @@ struct ehb_index {
   // build scratch
   DevBuf<uint32_t> b_edge_row, b_edge_src, b_row_cnt, b_row_fill, b_row_start, b_touched, b_seg_src, b_counters, b_ids;
   DevBuf<float> b_edge_dist, b_seg_dist, b_stage_in;
-  DevBuf<uint32_t> b_dst;
 
   // tuning (0 = auto)
-  uint32_t t_slots = 0, t_groups = 0, t_hash_bits = 0, t_wpb = 0, t_team = 0, t_latency = 0;
+  uint32_t t_slots = 0, t_groups = 0, t_hash_bits = 0, t_wpb = 0, t_team = 0;
 
   ~ehb_index() {
     if (ev0) cudaEventDestroy(ev0);
@@ -159,7 +158,6 @@ struct ehb_index {
     ehb::WalkCfg c;
     c.lcap = smem_list;
     c.staged = dpad > 256 ? 1 : 0;  // rows above 1 KB go through the TMA staging ring
-    c.latency_mode = 0;
     uint32_t vbytes = dpad * 4;
     uint32_t slots = std::max(4u, std::min(32u, 24576u / vbytes));
     uint32_t ng = 2;                      // two groups: math on one overlaps the copies of the other
@@ -735,8 +733,7 @@ int ehb_index_set_tuning(ehb_index* ix, uint32_t slots, uint32_t groups, uint32_
   ix->t_slots = slots;
   ix->t_groups = groups;
   ix->t_hash_bits = hash_bits;
-  ix->t_wpb = wpb & 0xFFu;
-  ix->t_latency = (wpb >> 8) & 3u;  // bits 8..9: 0 auto, 1 off, 2 on (latency mode)
+  ix->t_wpb = wpb;
   return EHB_OK;
 }
 

@@ -4,7 +4,7 @@
 
 namespace ehb {
 
-template <int LPV, int NQ, int KPL, int UX>
+template <int LPV, int NQ, int KPL>
 __global__ void __launch_bounds__(128) hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
                                                           uint32_t nq, uint32_t k, uint32_t ef,
                                                           uint64_t* __restrict__ out_labels,
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) hnsw_search_kernel(GraphView g, WalkCfg c
     __syncwarp();
     wc.evals = 1;
     greedy_descent<LPV, NQ>(c, g, qr, cur, curdist, g.max_level, 0, wc);
-    beam_search<LPV, NQ, KPL, true, UX>(c, g, qr, ul, cur, curdist, 0, ef, kInvalid, wc);
+    beam_search<LPV, NQ, KPL, true>(c, g, qr, ul, cur, curdist, 0, ef, kInvalid, wc);
   }
   // nearest-first output: extract the k closest in ascending order
   uint32_t found = 0;
@@ -54,14 +54,14 @@ __global__ void __launch_bounds__(128) hnsw_search_kernel(GraphView g, WalkCfg c
   }
 }
 
-template <int LPV, int NQ, int KPL, int UX>
+template <int LPV, int NQ, int KPL>
 cudaError_t launch_search_t(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
                             uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
                             uint32_t* stats, uint32_t wpb, cudaStream_t s) {
   uint32_t wsm = warp_smem_bytes(cfg, g.dpad);
   size_t smem = (size_t)wsm * wpb;
   dim3 grid((nq + wpb - 1) / wpb), block(32 * wpb);
-  auto kern = hnsw_search_kernel<LPV, NQ, KPL, UX>;
+  auto kern = hnsw_search_kernel<LPV, NQ, KPL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, block, smem, s>>>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wsm);
@@ -72,10 +72,10 @@ template <int LPV, int NQ>
 cudaError_t launch_search_kpl(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
                               uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
                               uint32_t* stats, uint32_t wpb, cudaStream_t s) {
-  // (A "latency mode" that kept a whole 2M-neighbour hop in flight per batch (UX = 2, ~168 registers) was
-  //  measured on C2: 0.446 ms vs 0.423 ms — no gain, so only UX = 1 is instantiated.)
+  // (Keeping a whole 2M-neighbour hop in flight per batch (~168 registers) was measured on C2:
+  //  0.446 ms vs 0.423 ms — no gain, so batches stay at 16 vectors.)
 #define EHB_KPL(K) \
-  return launch_search_t<LPV, NQ, K, 1>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wpb, s)
+  return launch_search_t<LPV, NQ, K>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wpb, s)
   if (ef <= 64) EHB_KPL(2);
   if (ef <= 128) EHB_KPL(4);
   if (ef <= 256) EHB_KPL(8);

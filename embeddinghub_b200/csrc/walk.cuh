@@ -5,9 +5,9 @@
 // fits the B200 memory system:
 //   * one warp owns one query (or one point being inserted);
 //   * an adjacency row is one 128 B line (2M = 32 u32, padded with kInvalid);
-//   * hnswlib's ef-bounded result heap and its candidate heap are ONE sorted
-//     array of 64-bit keys (ordered distance | expanded flag | id) held in
-//     registers, KPL keys per lane, maintained with warp shuffles;
+//   * hnswlib's ef-bounded result heap and its candidate heap are ONE unordered
+//     array of (ordered distance, id | expanded flag) held in registers, KPL
+//     entries per lane; the heap tops are warp reductions (redux.sync);
 //   * the visited set is a per-warp open-addressing table in shared memory;
 //   * distances of the unvisited neighbours of a node are evaluated together:
 //       - rows up to 1 KB (LPV = 8 lanes per vector): every lane issues its
@@ -44,7 +44,6 @@ struct WalkCfg {
   uint32_t G;          // vectors per TMA staging group (<= 32), LPV = 32 only
   uint32_t NG;         // staging groups (ring depth, <= 8)
   uint32_t staged;     // 1 when the TMA staging ring is allocated
-  uint32_t latency_mode;  // 1: direct-load shapes keep a whole hop's vectors in flight (small batches)
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -277,95 +276,13 @@ __device__ __forceinline__ void eval_staged(WarpCtx& c, const float* __restrict_
 }
 
 // cand_id[0..m) -> cand_dist[0..m): distances from the register-held query.
-// UX = 2 doubles the vectors in flight per batch on the direct-load path ("latency mode": a whole
-// 2M-neighbour hop in one round trip; needs ~64 more registers, used when the batch is small).
-template <int LPV, int NQ, int UX = 1>
+template <int LPV, int NQ>
 __device__ __forceinline__ void eval_candidates(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
                                                 uint32_t m, int metric) {
   if (LPV == 8)
-    eval_direct<NQ, UX * (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2))>(c, vecs, qr, m, metric);
+    eval_direct<NQ>(c, vecs, qr, m, metric);
   else
     eval_staged<NQ>(c, vecs, qr, m, metric);
-}
-
-// ---------------------------------------------------------------------------
-// Register-resident sorted key list: position i lives in lane i % 32, slot
-// i / 32; unused positions hold kMaxKey.
-// ---------------------------------------------------------------------------
-template <int KPL>
-__device__ __forceinline__ void rl_clear(uint64_t (&k)[KPL]) {
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) k[s] = kMaxKey;
-}
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// Insert `key` keeping at most `limit` entries.  Warp-uniform arguments.
-template <int KPL>
-__device__ __forceinline__ void rl_insert(uint64_t (&k)[KPL], uint64_t key, uint32_t limit, uint32_t lane) {
-  uint32_t pos = 0;
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) pos += __popc(__ballot_sync(0xffffffffu, k[s] < key));
-  if (pos >= limit) return;
-#pragma unroll
-  for (int s = KPL - 1; s >= 0; --s) {
-    if ((uint32_t)(s + 1) * 32u > pos) {  // warp-uniform: slots entirely below pos are untouched
-      uint64_t up = __shfl_up_sync(0xffffffffu, k[s], 1);
-      uint64_t carry = s > 0 ? shfl64(k[s > 0 ? s - 1 : 0], 31) : 0ull;
-      uint64_t shifted = lane == 0 ? carry : up;
-      uint32_t gi = (uint32_t)s * 32u + lane;
-      uint64_t nv = gi < pos ? k[s] : (gi == pos ? key : shifted);
-      k[s] = gi >= limit ? kMaxKey : nv;
-    }
-  }
-}
-// true when some entry carries this id (only needed once the visited table overflowed)
-template <int KPL>
-__device__ __forceinline__ bool rl_contains(const uint64_t (&k)[KPL], uint32_t id) {
-  bool hit = false;
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) hit |= (k[s] != kMaxKey) && key_id(k[s]) == id;
-  return __any_sync(0xffffffffu, hit);
-}
-// First unexpanded entry: returns its key (flag clear) and marks it expanded; kMaxKey if none.
-template <int KPL>
-__device__ __forceinline__ uint64_t rl_pop_unexpanded(uint64_t (&k)[KPL], uint32_t lane) {
-  uint64_t out = kMaxKey;
-  bool done = false;
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) {
-    if (!done) {
-      uint32_t b = __ballot_sync(0xffffffffu, k[s] != kMaxKey && !((uint32_t)k[s] & kExpandedFlag));
-      if (b) {
-        int l = __ffs(b) - 1;
-        out = shfl64(k[s], l);
-        if ((int)lane == l) k[s] |= kExpandedFlag;
-        done = true;
-      }
-    }
-  }
-  return out;
-}
-// key at position i (warp-uniform i)
-template <int KPL>
-__device__ __forceinline__ uint64_t rl_at(const uint64_t (&k)[KPL], uint32_t i) {
-  uint64_t v = k[0];
-#pragma unroll
-  for (int s = 1; s < KPL; ++s)
-    if ((i >> 5) == (uint32_t)s) v = k[s];
-  return shfl64(v, i & 31);
-}
-template <int KPL>
-__device__ __forceinline__ uint32_t rl_count(const uint64_t (&k)[KPL]) {
-  uint32_t n = 0;
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) n += __popc(__ballot_sync(0xffffffffu, k[s] != kMaxKey));
-  return n;
-}
-template <int KPL>
-__device__ __forceinline__ void rl_store(const uint64_t (&k)[KPL], uint64_t* dst, uint32_t lane) {
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) dst[s * 32 + lane] = k[s];
-  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
@@ -583,7 +500,7 @@ __device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, c
 // node).  The adjacency row of the likely next node (the closest unexpanded entry
 // before this hop's candidates are known) is requested ahead of the distance
 // evaluation, so its latency overlaps the vector loads.
-template <int LPV, int NQ, int KPL, bool PREFETCH, int UX = 1>
+template <int LPV, int NQ, int KPL, bool PREFETCH>
 __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], UList<KPL>& u,
                                             uint32_t ep, float epdist, int level, uint32_t ef, uint32_t exclude,
                                             WalkCounters& wc) {
@@ -618,7 +535,7 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       if (is_new) c.cand_id[__popc(mask & lanemask_lt())] = nb;
       __syncwarp();
       wc.evals += m;
-      eval_candidates<LPV, NQ, UX>(c, g.vecs, qr, m, g.metric);
+      eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
       // the speculative row has arrived by now: pull its neighbours' vectors towards L2 while this hop's
       // candidates are inserted (rows <= 1 KB only; a wrong guess costs bandwidth, not correctness)
       if (PREFETCH && LPV == 8 && spec_row != kInvalid) {
