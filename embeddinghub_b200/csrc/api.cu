@@ -118,7 +118,9 @@ struct ehb_index {
   DevBuf<float> bf_dist, bf_qpad;
   DevBuf<uint64_t> bf_part, bf_run;
   DevBuf<uint16_t> x_bf16, q_bf16;   // bf16 shadows for the tensor-core path
-  DevBuf<float> x_norm, q_norm2;
+  DevBuf<float> x_norm, q_norm2, bf_thr;
+  DevBuf<uint64_t> bf_cbuf;
+  DevBuf<uint32_t> bf_ccount;
   uint64_t bf16_rows = 0;            // rows of x_bf16 that are current (0 = stale)
 
   // build scratch
@@ -509,6 +511,20 @@ struct ehb_index {
       bctx.qnorm = q_norm2.p;
       bctx.xnorm = x_norm.p;
       bctx.kc = kc;
+      // fused selection state (EHB_BF16_UNFUSED=1 keeps the distance tiles in HBM: A/B switch)
+      static const bool unfused = getenv("EHB_BF16_UNFUSED") != nullptr;
+      bctx.fused = !unfused;
+      bctx.ccap = 2 * kc + 64;
+      CU(bf_thr.grow(nq, 0, -1, s));
+      CU(bf_cbuf.grow(nq * bctx.ccap, 0, -1, s));
+      CU(bf_ccount.grow(nq + 1, 0, 0, s));
+      bctx.thr = bf_thr.p;
+      bctx.cbuf = bf_cbuf.p;
+      bctx.ccount = bf_ccount.p;
+      bctx.overflow = bf_ccount.p + nq;
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      bctx.sms = sms;
     }
     CU(cudaEventRecord(ev0, s));
     CU(ehb::launch_bruteforce(vecs.p, dpad, dim, n, labels.p, metric == EHB_L2 ? 0 : 1, bf_qpad.p, nq, k, sc,

@@ -184,6 +184,209 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 1) tmem_dealloc(tmem_base, GN);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant with the selection fused into the epilogue: the Q x N distance tile never goes to HBM.
+// One CTA per SM walks the (query tile, base tile) list (query tile fastest, so the CTAs that share a base
+// tile run together); accumulators are double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  The epilogue compares every distance with the query's current threshold
+// thr[q] (its kc-th best bf16 distance so far) and appends the survivors (ordered distance | row index) to
+// the query's candidate buffer with one global atomic each; compact_candidates_kernel folds the buffer into
+// the running top-kc and tightens thr between chunks.  With chunk sizes that double, a chunk admits about kc
+// candidates per query, so the buffer (capacity 2 kc + 64) practically never overflows; if it does the
+// driver re-runs that chunk through the unfused path.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kFusedSmem = GSTAGES * (kStageBytesA + kStageBytesB) + 1024 + 256;
+static cudaError_t make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t dpad, uint32_t box_rows);
+
+__global__ void __launch_bounds__(192, 1)
+    bf16_topk_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                          uint32_t kblocks, int metric, const float* __restrict__ qnorm,
+                          const float* __restrict__ xnorm, uint64_t nq, uint64_t n_lo, uint64_t n_hi,
+                          const float* __restrict__ thr, uint64_t* __restrict__ cbuf, uint32_t* __restrict__ ccount,
+                          uint32_t ccap) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + GSTAGES * kStageBytesA;
+  uint64_t* full = (uint64_t*)(smem + GSTAGES * (kStageBytesA + kStageBytesB));
+  uint64_t* empty = full + GSTAGES;
+  uint64_t* tmem_full = empty + GSTAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t q_tiles = (nq + GM - 1) / GM, n_tiles = (n_hi - n_lo + GN - 1) / GN;
+  const uint64_t tiles = q_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < GSTAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+    for (int a = 0; a < 2; ++a) mbar_init(&tmem_full[a], 1), mbar_init(&tmem_empty[a], 4);
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * GN);  // 512 columns: two accumulator stages
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint64_t tq = t % q_tiles, tn = t / q_tiles;
+        for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
+          uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kStageBytesA + kStageBytesB);
+          tma_load_2d(sA + s * kStageBytesA, &map_q, (int)(kb * GK), (int)(tq * GM), &full[s]);
+          tma_load_2d(sB + s * kStageBytesB, &map_x, (int)(kb * GK), (int)(n_lo + tn * GN), &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(GM, GN);
+      uint32_t it = 0, ti = 0;
+      for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], aph ^ 1u);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
+          uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          uint64_t da = make_smem_desc(sA + s * kStageBytesA), db = make_smem_desc(sB + s * kStageBytesB);
+#pragma unroll
+          for (uint32_t k4 = 0; k4 < GK / 16; ++k4)
+            umma_bf16(tmem_base + acc * GN, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const uint32_t quarter = warp & 3u;
+    uint32_t ti = 0;
+    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++ti) {
+      const uint64_t tq = t % q_tiles, tn = t / q_tiles;
+      const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+      const uint64_t q = tq * GM + quarter * 32u + lane;
+      const bool qok = q < nq;
+      const float tau = qok ? thr[q] : -INFINITY;
+      const float qn2 = (metric == 0 && qok) ? qnorm[q] : 0.f;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      for (uint32_t c0 = 0; c0 < GN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + acc * GN + ((quarter * 32u) << 16) + c0, r);
+        const uint64_t nbase = n_lo + tn * GN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float dot = __uint_as_float(r[j]);
+          float d;
+          if (metric == 0) {
+            float xn = nbase + j < n_hi ? xnorm[nbase + j] : 0.f;
+            d = fmaxf(qn2 + xn - 2.0f * dot, 0.f);
+          } else {
+            d = 1.0f - dot;
+          }
+          if (d < tau && nbase + j < n_hi) {
+            uint32_t pos = atomicAdd(&ccount[q], 1u);
+            if (pos < ccap) cbuf[q * ccap + pos] = make_key(d, (uint32_t)(nbase + j));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * GN);
+}
+
+// One warp per query: fold the candidate buffer into the running top-kc (sorted), publish the new
+// threshold, reset the counter; overflow[0] != 0 tells the driver the buffer was too small.
+__global__ void compact_candidates_kernel(uint64_t* __restrict__ run_keys, uint64_t* __restrict__ cbuf,
+                                          uint32_t* __restrict__ ccount, uint32_t ccap, uint32_t kc, uint64_t nq,
+                                          float* __restrict__ thr, uint32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const uint64_t q = (uint64_t)blockIdx.x * wpb + w;
+  if (q >= nq) return;
+  WarpCtx c;
+  c.lane = lane_id();
+  c.keys = (uint64_t*)smem + (size_t)w * align_up(kc, 32);
+  uint64_t* run = run_keys + q * kc;
+  uint32_t cnt = 0;
+  for (uint32_t i0 = 0; i0 < kc; i0 += 32) {
+    uint32_t i = i0 + c.lane;
+    uint64_t key = i < kc ? run[i] : kMaxKey;
+    if (i < kc) c.keys[i] = key;
+    cnt += __popc(__ballot_sync(0xffffffffu, key != kMaxKey));
+  }
+  __syncwarp();
+  c.cnt = cnt;  // run lists are sorted with kMaxKey padding at the end
+  uint32_t m = ccount[q];
+  if (m > ccap) {
+    if (c.lane == 0) atomicExch(overflow, 1u);
+    m = ccap;
+  }
+  for (uint32_t j0 = 0; j0 < m; j0 += 32) {
+    uint32_t j = j0 + c.lane;
+    uint64_t key = j < m ? cbuf[q * ccap + j] : kMaxKey;
+    uint32_t qual = __ballot_sync(0xffffffffu, j < m && (c.cnt < kc || key < c.keys[kc - 1]));
+    while (qual) {
+      int l = __ffs(qual) - 1;
+      qual &= qual - 1;
+      uint64_t kj = __shfl_sync(0xffffffffu, key, l);
+      if (c.cnt >= kc && kj >= c.keys[kc - 1]) continue;
+      list_insert(c, kj, kc);
+    }
+  }
+  __syncwarp();
+  for (uint32_t i = c.lane; i < kc; i += 32) run[i] = i < c.cnt ? c.keys[i] : kMaxKey;
+  if (c.lane == 0) {
+    thr[q] = c.cnt >= kc ? key_dist(c.keys[kc - 1]) : INFINITY;
+    ccount[q] = 0;
+  }
+}
+
+cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* x_bf16, uint64_t x_rows, uint32_t dpad,
+                                   int metric, const float* qnorm, const float* xnorm, uint64_t n_lo, uint64_t n_hi,
+                                   float* thr, uint64_t* cbuf, uint32_t* ccount, uint32_t ccap, uint64_t* run_keys,
+                                   uint32_t kc, uint32_t* overflow, int sms, cudaStream_t s) {
+  if (dpad % GK != 0) return cudaErrorInvalidValue;
+  CUtensorMap mq, mx;
+  cudaError_t e;
+  if ((e = make_map(&mq, q_bf16, nq, dpad, GM)) != cudaSuccess) return e;
+  if ((e = make_map(&mx, x_bf16, x_rows, dpad, GN)) != cudaSuccess) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(bf16_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (n_hi > n_lo) {
+    uint64_t tiles = ((nq + GM - 1) / GM) * ((n_hi - n_lo + GN - 1) / GN);
+    unsigned grid = (unsigned)(tiles < (uint64_t)sms ? tiles : (uint64_t)sms);
+    bf16_topk_gemm_kernel<<<grid, 192, kFusedSmem, s>>>(mq, mx, dpad / GK, metric == 0 ? 0 : 1, qnorm, xnorm, nq, n_lo,
+                                                      n_hi, thr, cbuf, ccount, ccap);
+  }
+  // kc == 0: only the GEMM (used by nothing); otherwise fold the survivors
+  const uint32_t wpb = 4;
+  size_t smem = (size_t)wpb * align_up(kc, 32) * 8;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(compact_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  compact_candidates_kernel<<<(unsigned)((nq + wpb - 1) / wpb), 32 * wpb, smem, s>>>(run_keys, cbuf, ccount, ccap, kc,
+                                                                                     nq, thr, overflow);
+  return cudaGetLastError();
+}
+
 // ---- fp32 -> bf16 rows (+ squared norms of the rounded values) ------------------------------------
 __global__ void to_bf16_rows_kernel(const float* __restrict__ in, uint32_t in_stride, __nv_bfloat16* __restrict__ out,
                                     float* __restrict__ norms, uint64_t n, uint32_t dpad) {

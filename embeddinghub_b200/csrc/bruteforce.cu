@@ -200,33 +200,70 @@ cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, ui
     uint64_t tot = nq * ksel;
     bf_fill_keys_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(sc.run_keys, tot);
   }
-  for (uint64_t q0 = 0; q0 < nq; q0 += sc.qb) {
-    uint64_t qn = sc.qb < nq - q0 ? sc.qb : nq - q0;
-    for (uint64_t n0 = 0; n0 < n; n0 += sc.nc) {
-      uint64_t nn = sc.nc < n - n0 ? sc.nc : n - n0;
-      if (bf) {
-        e = launch_bf16_dist_tile(bf->q_bf16, nq, bf->x_bf16, n, dpad, metric, bf->qnorm, bf->xnorm, q0, qn, n0, nn,
-                                  sc.dist, sc.nc, s);
-        if (e != cudaSuccess) return e;
-      } else {
-        dim3 grid((unsigned)((nn + TN - 1) / TN), (unsigned)((qn + TQ - 1) / TQ));
-        if (metric == 0)
-          bf_dist_kernel<0><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
-        else
-          bf_dist_kernel<1><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
+  // distance tiles -> HBM -> per-slice select -> merge into run_keys, over base rows [nb, ne)
+  auto unfused_range = [&](uint64_t nb, uint64_t ne) -> cudaError_t {
+    for (uint64_t q0 = 0; q0 < nq; q0 += sc.qb) {
+      uint64_t qn = sc.qb < nq - q0 ? sc.qb : nq - q0;
+      for (uint64_t n0 = nb; n0 < ne; n0 += sc.nc) {
+        uint64_t nn = sc.nc < ne - n0 ? sc.nc : ne - n0;
+        if (bf) {
+          cudaError_t e2 = launch_bf16_dist_tile(bf->q_bf16, nq, bf->x_bf16, n, dpad, metric, bf->qnorm, bf->xnorm, q0,
+                                                 qn, n0, nn, sc.dist, sc.nc, s);
+          if (e2 != cudaSuccess) return e2;
+        } else {
+          dim3 grid((unsigned)((nn + TN - 1) / TN), (unsigned)((qn + TQ - 1) / TQ));
+          if (metric == 0)
+            bf_dist_kernel<0><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
+          else
+            bf_dist_kernel<1><<<grid, 256, 0, s>>>(qpad, vecs, dpad, q0, qn, n0, nn, sc.dist, sc.nc);
+        }
+        // one warp per (query, slice): as few slices as still fill the machine (~4096 warps) — every slice
+        // sorts its own top-k from scratch, so slices multiply the insert work
+        uint64_t want_sl = (4096 + qn - 1) / qn;
+        if (want_sl > nn / 1024) want_sl = nn / 1024 ? nn / 1024 : 1;
+        uint32_t slices = (uint32_t)(want_sl < sc.slices ? want_sl : sc.slices);
+        if (slices == 0) slices = 1;
+        uint64_t jobs = qn * slices;
+        bf_select_kernel<<<(unsigned)((jobs + wpb - 1) / wpb), 32 * wpb, smem, s>>>(
+            sc.dist, sc.nc, nn, n0, qn, slices, ksel, sc.part_keys, sc.run_keys, q0);
+        bf_merge_kernel<<<(unsigned)((qn + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.run_keys, sc.part_keys, q0, qn,
+                                                                                slices, ksel);
       }
-      // one warp per (query, slice): as few slices as still fill the machine (~4096 warps) — every slice
-      // sorts its own top-k from scratch, so slices multiply the insert work
-      uint64_t want_sl = (4096 + qn - 1) / qn;
-      if (want_sl > nn / 1024) want_sl = nn / 1024 ? nn / 1024 : 1;
-      uint32_t slices = (uint32_t)(want_sl < sc.slices ? want_sl : sc.slices);
-      if (slices == 0) slices = 1;
-      uint64_t jobs = qn * slices;
-      bf_select_kernel<<<(unsigned)((jobs + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.dist, sc.nc, nn, n0, qn, slices,
-                                                                                 ksel, sc.part_keys, sc.run_keys, q0);
-      bf_merge_kernel<<<(unsigned)((qn + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.run_keys, sc.part_keys, q0, qn,
-                                                                              slices, ksel);
     }
+    return cudaGetLastError();
+  };
+  if (bf && bf->fused && n > 8192) {
+    // bootstrap thresholds on the first rows, then fused chunks that double in size: a chunk as large as
+    // everything seen so far admits about kc survivors per query
+    const uint64_t s0 = 8192;
+    if ((e = cudaMemsetAsync(bf->ccount, 0, nq * 4, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bf->overflow, 0, 4, s)) != cudaSuccess) return e;
+    if ((e = unfused_range(0, s0)) != cudaSuccess) return e;
+    // compaction with empty buffers publishes thr[q] from the bootstrap lists
+    e = launch_bf16_topk_chunk(bf->q_bf16, nq, bf->x_bf16, n, dpad, metric, bf->qnorm, bf->xnorm, 0, 0, bf->thr,
+                               bf->cbuf, bf->ccount, bf->ccap, sc.run_keys, ksel, bf->overflow, bf->sms, s);
+    if (e != cudaSuccess) return e;
+    uint64_t seen = s0;
+    while (seen < n) {
+      uint64_t chunk = n - seen < seen ? n - seen : seen;
+      e = launch_bf16_topk_chunk(bf->q_bf16, nq, bf->x_bf16, n, dpad, metric, bf->qnorm, bf->xnorm, seen,
+                                 seen + chunk, bf->thr, bf->cbuf, bf->ccount, bf->ccap, sc.run_keys, ksel,
+                                 bf->overflow, bf->sms, s);
+      if (e != cudaSuccess) return e;
+      uint32_t ovf = 0;
+      if ((e = cudaMemcpyAsync(&ovf, bf->overflow, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+      if (ovf) {  // a candidate buffer filled up: redo this chunk through the unfused path (always exact)
+        if ((e = cudaMemsetAsync(bf->overflow, 0, 4, s)) != cudaSuccess) return e;
+        if ((e = unfused_range(seen, seen + chunk)) != cudaSuccess) return e;
+        e = launch_bf16_topk_chunk(bf->q_bf16, nq, bf->x_bf16, n, dpad, metric, bf->qnorm, bf->xnorm, 0, 0, bf->thr,
+                                   bf->cbuf, bf->ccount, bf->ccap, sc.run_keys, ksel, bf->overflow, bf->sms, s);
+        if (e != cudaSuccess) return e;
+      }
+      seen += chunk;
+    }
+  } else {
+    if ((e = unfused_range(0, n)) != cudaSuccess) return e;
   }
   if (bf)
     return launch_rerank(sc.run_keys, ksel, qpad, vecs, dpad, dim, metric, labels, nq, k, out_labels, out_dists,

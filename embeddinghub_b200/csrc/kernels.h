@@ -48,7 +48,19 @@ struct Bf16Ctx {
   const float* qnorm;   // [nq] squared norms of the rounded queries (L2 only)
   const float* xnorm;   // [n]
   uint32_t kc;          // candidates kept per query before the fp32 re-rank (>= k)
+  // fused selection (epilogue filter): per-query threshold, candidate buffer [nq][ccap], counters, flag
+  float* thr;
+  uint64_t* cbuf;
+  uint32_t* ccount;
+  uint32_t ccap;
+  uint32_t* overflow;   // device flag
+  int sms;
+  bool fused;
 };
+cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* x_bf16, uint64_t x_rows, uint32_t dpad,
+                                   int metric, const float* qnorm, const float* xnorm, uint64_t n_lo, uint64_t n_hi,
+                                   float* thr, uint64_t* cbuf, uint32_t* ccount, uint32_t ccap, uint64_t* run_keys,
+                                   uint32_t kc, uint32_t* overflow, int sms, cudaStream_t s);
 cudaError_t launch_to_bf16(const float* in, uint32_t in_stride, void* out_bf16, float* norms, uint64_t n, uint32_t dpad,
                            cudaStream_t s);
 cudaError_t launch_bf16_dist_tile(const void* q_bf16, uint64_t q_rows, const void* x_bf16, uint64_t x_rows,
