@@ -8,10 +8,10 @@ SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := embeddinghub_b200/libehb200.so
 
-all: $(LIB) oracle tests/cpp/index_test_cc
+all: $(LIB) oracle tests/cpp/ann_index_cases
 
-# the reference's index_test.cc cases against the C++ drop-in twin (run by tests/test_gpu_host.py)
-tests/cpp/index_test_cc: tests/cpp/index_test.cc include/ehb200_ann_index.hpp $(LIB)
+# the reference's ANNIndex unit-test cases against the C++ drop-in twin (run by tests/test_gpu_host.py)
+tests/cpp/ann_index_cases: tests/cpp/ann_index_cases.cc include/ehb200_ann_index.hpp $(LIB)
 	g++ -std=c++17 -O2 -Iinclude $< -Lembeddinghub_b200 -lehb200 -Wl,-rpath,'$$ORIGIN/../../embeddinghub_b200' -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/kernels.h include/ehb200.h

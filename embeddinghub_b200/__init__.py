@@ -8,6 +8,6 @@ that path.
 from ._native import EhbError, NativeIndex, NO_LABEL, lib  # noqa: F401
 from .ann_index import ANNIndex  # noqa: F401
 from .hub import EmbeddingHub, HubError  # noqa: F401
-from . import offlinehub  # noqa: F401
+from . import offline  # noqa: F401
 
-__all__ = ["ANNIndex", "EmbeddingHub", "HubError", "NativeIndex", "EhbError", "NO_LABEL", "lib", "offlinehub"]
+__all__ = ["ANNIndex", "EmbeddingHub", "HubError", "NativeIndex", "EhbError", "NO_LABEL", "lib", "offline"]

@@ -8,13 +8,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import embeddinghub_b200 as ehb  # noqa: E402
-from embeddinghub_b200.offlinehub import Index  # noqa: E402
+from embeddinghub_b200.offline import Index  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_cpp_annindex_twin_runs_reference_index_test_cases():
-    exe = os.path.join(ROOT, "tests", "cpp", "index_test_cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "ann_index_cases")
     assert os.path.exists(exe), "run make"
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr

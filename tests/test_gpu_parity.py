@@ -350,3 +350,40 @@ def test_merge_topk_packed_dev():
     order = np.argsort(flat_d, axis=1, kind="stable")[:, :k]
     assert np.array_equal(od.cpu().numpy(), np.take_along_axis(flat_d, order, 1))
     assert np.array_equal(ol.cpu().numpy().view(np.uint64), np.take_along_axis(flat_l, order, 1))
+
+
+# ---- BASELINE.json configs[1] at full size: size-independent properties ---------------------------------
+def test_c2_full_size_properties():
+    """N=1M d=128 Q=1000 k=10 ef=64 L2 (the bench workload): the oracle cannot BUILD this in test time, so the
+    walk is checked through properties — sortedness, uniqueness, full counts, idempotence, returned distances
+    equal to the exact distances of the returned ids, recall against the exact kernel — and, for the
+    hnswlib-order walk (one warp per query), id equality with the CPU oracle walking the SAME exported graph."""
+    from bench import gen, BASE_SEED, QUERY_SEED
+
+    n, d, nq, k, ef = 1_000_000, 128, 1000, 10, 64
+    base, q = gen(n, d, BASE_SEED), gen(nq, d, QUERY_SEED)
+    ix = ehb.NativeIndex(d, capacity=n)
+    ix.add(base)
+    ix.build()
+    gt, gtd, _ = ix.search_bruteforce(q, k)
+    for width in (1, 0):                                   # exact order, then the automatic (team) mode
+        ix.set_search_width(width)
+        l, dd, c = ix.search(q, k, ef=ef)
+        l2, dd2, _ = ix.search(q, k, ef=ef)
+        assert np.array_equal(l, l2) and np.array_equal(dd, dd2)          # idempotent / deterministic
+        assert np.all(c == k) and np.all(np.diff(dd, axis=1) >= 0)
+        assert all(len(set(r.tolist())) == k for r in l)
+        ex = ((base[l.astype(np.int64)] - q[:, None, :]) ** 2).sum(-1)    # exact distances of the returned ids
+        np.testing.assert_allclose(dd, ex, rtol=RTOL, atol=1e-5)
+        rec = recall(l, gt)
+        assert rec >= 0.20, rec                                           # iid Gaussian d=128: hard for any graph
+        if width == 1:
+            l_seq, rec_seq = l, rec
+        else:
+            assert rec >= rec_seq - 0.003
+    o = orc.OracleHNSW(d, "l2", n)
+    o.import_graph(ix.export_graph())
+    ol, od, _ = o.search(q[:200], k, ef=ef, threads=8)
+    assert np.mean(ol == l_seq[:200]) >= 0.995
+    st = ix.stats()
+    assert st["size"] == n and st["max_level"] >= 3
