@@ -431,14 +431,14 @@ struct ehb_index {
     uint32_t ef_eff = std::max(ef_in ? ef_in : ef, k);
     if (ef_eff > ehb::kMaxEf) return fail(EHB_ERR_INVALID, "max(ef, k) must be <= 512");
     RET(build());
-    // Warps per query: two when every query still fits one wave (7 CTAs of 64 threads per SM), i.e. when
-    // the batch is too small to fill the GPU with one warp per query (C2: 0.284 ms vs 0.409 ms); for
-    // larger batches one warp per query wins (C5 shape, Q=10k: 9.2 ms vs 10.7 ms).  Rows <= 1 KB, ef <= 256.
+    // Warps per query (rows <= 1 KB, ef <= 256): four while 3 CTAs of 128 threads per SM hold every query (small
+    // online batches; Q=1: 135 us vs 252 us with one warp), two while 7 CTAs of 64 threads do (C2, Q=1000:
+    // 0.288 ms vs 0.409 ms), else one warp per query (C5 shape, Q=10k: 9.2 ms vs 10.7 ms with two).
     uint32_t team = t_team;
     if (team == 0) {
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-      team = nq <= (uint64_t)sms * 7 ? 2 : 1;
+      team = nq <= (uint64_t)sms * 3 ? 4 : (nq <= (uint64_t)sms * 7 ? 2 : 1);
     }
     if (dpad > 256 || ef_eff > 256) team = 1;
     ehb::WalkCfg cfg = walk_cfg(ef_eff, 0, nq * team, team);

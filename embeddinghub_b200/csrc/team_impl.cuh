@@ -33,7 +33,7 @@ __host__ __device__ inline uint32_t team_smem_bytes(uint32_t hash_size, uint32_t
 }
 
 template <int NQ, int KPL, int T, int U>
-__global__ void __launch_bounds__(T * 32, 7) hnsw_search_team_kernel(GraphView g, uint32_t hash_size,
+__global__ void __launch_bounds__(T * 32, (T == 4 && U * NQ >= 16) ? 3 : 7) hnsw_search_team_kernel(GraphView g, uint32_t hash_size,
                                                                      const float* __restrict__ queries, uint32_t nq,
                                                                      uint32_t k, uint32_t ef,
                                                                      uint64_t* __restrict__ out_labels,
