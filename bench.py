@@ -43,6 +43,9 @@ WORKLOADS = {
                desc="HNSW N=10M d=768 Q=10k k=10 ef=128 InnerProduct (BASELINE.json configs[2])"),
     "c5s": dict(N=1_000_000, d=128, Q=10000, k=100, ef=256, metric="cosine",
                 desc="C5 shape at N=1M per GPU: d=128 Q=10k k=100 ef=256 cosine"),
+    "c5": dict(N=12_500_000, d=128, Q=10000, k=100, ef=256, metric="cosine",
+               desc="HNSW N=100M d=128 Q=10k k=100 ef=256 cosine range-sharded over 8 GPUs = 12.5M per GPU "
+                    "(BASELINE.json configs[4]; with fewer ranks the total shrinks accordingly)"),
     # brute force on the bf16 tensor-core path (tcgen05 GEMM + fp32 re-rank); recall is measured against the
     # exact fp32 path
     "c4s": dict(N=1_000_000, d=768, Q=4096, k=100, ef=0, metric="ip", brute="bf16",
