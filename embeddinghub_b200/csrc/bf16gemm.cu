@@ -363,12 +363,8 @@ cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* 
   cudaError_t e;
   if ((e = make_map(&mq, q_bf16, nq, dpad, GM)) != cudaSuccess) return e;
   if ((e = make_map(&mx, x_bf16, x_rows, dpad, GN)) != cudaSuccess) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(bf16_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  e = cudaFuncSetAttribute(bf16_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+  if (e != cudaSuccess) return e;
   if (n_hi > n_lo) {
     uint64_t tiles = ((nq + GM - 1) / GM) * ((n_hi - n_lo + GN - 1) / GN);
     unsigned grid = (unsigned)(tiles < (uint64_t)sms ? tiles : (uint64_t)sms);
@@ -446,12 +442,8 @@ cudaError_t launch_bf16_dist_tile(const void* q_bf16, uint64_t q_rows, const voi
   cudaError_t e;
   if ((e = make_map(&mq, q_bf16, q_rows, dpad, GM)) != cudaSuccess) return e;
   if ((e = make_map(&mx, x_bf16, x_rows, dpad, GN)) != cudaSuccess) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(bf16_dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  e = cudaFuncSetAttribute(bf16_dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+  if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((qn + GM - 1) / GM), (unsigned)((nn + GN - 1) / GN));
   bf16_dist_gemm_kernel<<<grid, 192, kGemmSmem, s>>>(mq, mx, dpad / GK, metric == 0 ? 0 : 1, qnorm, xnorm, q0, qn, n0,
                                                     nn, dist, ldd);
