@@ -387,3 +387,31 @@ def test_c2_full_size_properties():
     assert np.mean(ol == l_seq[:200]) >= 0.995
     st = ix.stats()
     assert st["size"] == n and st["max_level"] >= 3
+
+
+def test_walk_edge_cases_empty_tiny_and_ragged():
+    """Empty index, fewer points than k, a single point, k == 1, and a batch whose size is not a multiple of
+    anything — the shapes the reference's unit tests and its `num > count` bug (index.cc:42-50) touch."""
+    d = 6
+    ix = ehb.NativeIndex(d, capacity=4)
+    q = np.random.default_rng(0).standard_normal((7, d), dtype=np.float32)
+    for width in (1, 2, 4):
+        ix.set_search_width(width)
+        l, dd, c = ix.search(q, 5, ef=10)
+        assert np.all(l == ehb.NO_LABEL) and np.all(np.isinf(dd)) and np.all(c == 0)
+    base = np.random.default_rng(1).standard_normal((3, d), dtype=np.float32)
+    ix.add(base[:1])
+    for width in (1, 2, 4):
+        ix.set_search_width(width)
+        l, dd, c = ix.search(q, 5, ef=10)
+        assert np.all(c == 1) and np.all(l[:, 0] == 0) and np.all(l[:, 1:] == ehb.NO_LABEL)
+    ix.add(base[1:])
+    ex, exd = orc.bruteforce(base, q, 3, "l2")
+    for width in (1, 2, 4):
+        ix.set_search_width(width)
+        l, dd, c = ix.search(q, 5, ef=10)          # k > n: 3 results, then padding
+        assert np.all(c == 3) and np.array_equal(l[:, :3], ex) and np.all(l[:, 3:] == ehb.NO_LABEL)
+        np.testing.assert_allclose(dd[:, :3], exd, rtol=RTOL, atol=1e-6)
+        assert np.all(np.isinf(dd[:, 3:]))
+        l1, _, c1 = ix.search(q[:1], 1)            # ef defaults to 10 -> max(10, k)
+        assert c1[0] == 1 and l1[0, 0] == ex[0, 0]
