@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace ehb {
@@ -307,6 +309,177 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 1) tmem_dealloc(tmem_base, 2 * GN);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 2-CTA form of the fused kernel (cta_group::2): a cluster of two SMs owns a 256 x 256 tile.  Each CTA
+// stages its own 128 query rows and HALF of the base tile (128 rows) per k-block — 32 KB instead of 48 KB for
+// the same tensor-pipe time — so the six-stage ring covers the L2 -> SM latency that bounds the 1-CTA kernel.
+// The leader CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256); both CTAs' TMA loads complete on the
+// leader's `full` barrier; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to both CTAs; the
+// non-leader's epilogue warps release the accumulator stage on the leader's `tmem_empty` barrier remotely.
+// Opt-in (EHB_GEMM_2CTA=1): measured on C4-shaped chunks it reaches 765 TFLOP/s in-kernel vs 826 TFLOP/s
+// for the 1-CTA kernel — both sit on the L2 -> SM operand traffic (92 resp. 61 B/clk/SM requested against
+// a chip-wide LTS cap of ~6.3 KB/clk), so the next step is TMA multicast across a larger cluster, not this.
+// ---------------------------------------------------------------------------------------------------
+constexpr int G2STAGES = 6;
+constexpr uint32_t kStage2 = (GM * GK * 2) + (128 * GK * 2);  // A 128x64 + B-half 128x64 bf16 = 32 KB
+constexpr uint32_t kFused2Smem = G2STAGES * kStage2 + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  // both CTAs execute this; clearing the peer bit makes the transaction bytes land on CTA 0's barrier
+  uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "l"(0x1000000000000000ull)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+    bf16_topk_gemm2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                           uint32_t kblocks, int metric, const float* __restrict__ qnorm,
+                           const float* __restrict__ xnorm, uint64_t nq, uint64_t n_lo, uint64_t n_hi,
+                           const float* __restrict__ thr, uint64_t* __restrict__ cbuf, uint32_t* __restrict__ ccount,
+                           uint32_t ccap) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                   // [stage][128 x 64]
+  unsigned char* sB = smem + G2STAGES * (GM * GK * 2);        // [stage][128 x 64] (this CTA's half of the base tile)
+  uint64_t* full = (uint64_t*)(smem + G2STAGES * kStage2);
+  uint64_t* empty = full + G2STAGES;
+  uint64_t* tmem_full = empty + G2STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2] (used in the leader)
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint64_t q_tiles = (nq + 2 * GM - 1) / (2 * GM), n_tiles = (n_hi - n_lo + GN - 1) / GN;
+  const uint64_t tiles = q_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < G2STAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+    for (int a = 0; a < 2; ++a) mbar_init(&tmem_full[a], 1), mbar_init(&tmem_empty[a], 8);
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(2u * GN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint64_t t = cluster_id; t < tiles; t += n_clusters) {
+        const uint64_t tq = t % q_tiles, tn = t / q_tiles;
+        for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
+          uint32_t s = it % G2STAGES, ph = (it / G2STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * kStage2);  // both CTAs' bytes land here
+          tma_load_2d_2sm(sA + s * (GM * GK * 2), &map_q, (int)(kb * GK), (int)(tq * 2 * GM + rank * GM), &full[s]);
+          tma_load_2d_2sm(sB + s * (128 * GK * 2), &map_x, (int)(kb * GK), (int)(n_lo + tn * GN + rank * 128),
+                          &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * GM, GN);
+      uint32_t it = 0, ti = 0;
+      for (uint64_t t = cluster_id; t < tiles; t += n_clusters, ++ti) {
+        const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], aph ^ 1u);
+        tc_fence_after();
+        for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
+          uint32_t s = it % G2STAGES, ph = (it / G2STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          uint64_t da = make_smem_desc(sA + s * (GM * GK * 2)), db = make_smem_desc(sB + s * (128 * GK * 2));
+#pragma unroll
+          for (uint32_t k4 = 0; k4 < GK / 16; ++k4)
+            umma_bf16_2sm(tmem_base + acc * GN, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const uint32_t quarter = warp & 3u;
+    uint32_t ti = 0;
+    for (uint64_t t = cluster_id; t < tiles; t += n_clusters, ++ti) {
+      const uint64_t tq = t % q_tiles, tn = t / q_tiles;
+      const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+      const uint64_t q = tq * 2 * GM + rank * GM + quarter * 32u + lane;
+      const bool qok = q < nq;
+      const float tau = qok ? thr[q] : -INFINITY;
+      const float qn2 = (metric == 0 && qok) ? qnorm[q] : 0.f;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      for (uint32_t c0 = 0; c0 < GN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + acc * GN + ((quarter * 32u) << 16) + c0, r);
+        const uint64_t nbase = n_lo + tn * GN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float dot = __uint_as_float(r[j]);
+          float d;
+          if (metric == 0) {
+            float xn = nbase + j < n_hi ? xnorm[nbase + j] : 0.f;
+            d = fmaxf(qn2 + xn - 2.0f * dot, 0.f);
+          } else {
+            d = 1.0f - dot;
+          }
+          if (d < tau && nbase + j < n_hi) {
+            uint32_t pos = atomicAdd(&ccount[q], 1u);
+            if (pos < ccap) cbuf[q * ccap + pos] = make_key(d, (uint32_t)(nbase + j));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tmem_empty[acc], 0);  // the leader's MMA thread owns the accumulator hand-off
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * GN) : "memory");
+}
+
 // One warp per query: fold the candidate buffer into the running top-kc (sorted), publish the new
 // threshold, reset the counter; overflow[0] != 0 tells the driver the buffer was too small.
 __global__ void compact_candidates_kernel(uint64_t* __restrict__ run_keys, uint64_t* __restrict__ cbuf,
@@ -366,10 +539,34 @@ cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* 
   e = cudaFuncSetAttribute(bf16_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
   if (e != cudaSuccess) return e;
   if (n_hi > n_lo) {
-    uint64_t tiles = ((nq + GM - 1) / GM) * ((n_hi - n_lo + GN - 1) / GN);
-    unsigned grid = (unsigned)(tiles < (uint64_t)sms ? tiles : (uint64_t)sms);
-    bf16_topk_gemm_kernel<<<grid, 192, kFusedSmem, s>>>(mq, mx, dpad / GK, metric == 0 ? 0 : 1, qnorm, xnorm, nq, n_lo,
-                                                      n_hi, thr, cbuf, ccount, ccap);
+    static const bool two_cta = getenv("EHB_GEMM_2CTA") != nullptr;
+    if (two_cta) {
+      if ((e = make_map(&mx, x_bf16, x_rows, dpad, 128)) != cudaSuccess) return e;  // each CTA stages half a base tile
+      e = cudaFuncSetAttribute(bf16_topk_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFused2Smem);
+      if (e != cudaSuccess) return e;
+      uint64_t tiles = ((nq + 2 * GM - 1) / (2 * GM)) * ((n_hi - n_lo + GN - 1) / GN);
+      unsigned clusters = (unsigned)(tiles < (uint64_t)(sms / 2) ? tiles : (uint64_t)(sms / 2));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(clusters * 2);
+      cfg.blockDim = dim3(192);
+      cfg.dynamicSmemBytes = kFused2Smem;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, bf16_topk_gemm2_kernel, mq, mx, dpad / GK, metric == 0 ? 0 : 1, qnorm, xnorm,
+                             (uint64_t)nq, n_lo, n_hi, (const float*)thr, cbuf, ccount, ccap);
+      if (e != cudaSuccess) return e;
+    } else {
+      uint64_t tiles = ((nq + GM - 1) / GM) * ((n_hi - n_lo + GN - 1) / GN);
+      unsigned grid = (unsigned)(tiles < (uint64_t)sms ? tiles : (uint64_t)sms);
+      bf16_topk_gemm_kernel<<<grid, 192, kFusedSmem, s>>>(mq, mx, dpad / GK, metric == 0 ? 0 : 1, qnorm, xnorm, nq,
+                                                        n_lo, n_hi, thr, cbuf, ccount, ccap);
+    }
   }
   // kc == 0: only the GEMM (used by nothing); otherwise fold the survivors
   const uint32_t wpb = 4;
