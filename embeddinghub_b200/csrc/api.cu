@@ -56,16 +56,13 @@ struct DevBuf {
     T* np = nullptr;
     cudaError_t e = cudaMalloc(&np, want * sizeof(T));
     if (e != cudaSuccess) return e;
-    if (keep && p) {
-      e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return e;
+    if (keep && p) e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && fill >= 0) e = cudaMemsetAsync(np + keep, fill, (want - keep) * sizeof(T), s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      cudaFree(np);  // the old buffer stays valid
+      return e;
     }
-    if (fill >= 0) {
-      e = cudaMemsetAsync(np + keep, fill, (want - keep) * sizeof(T), s);
-      if (e != cudaSuccess) return e;
-    }
-    e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return e;
     if (p) cudaFree(p);
     p = np;
     n = want;
