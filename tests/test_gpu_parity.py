@@ -436,3 +436,43 @@ def test_bf16_bruteforce_two_cta_variant():
     env = dict(os.environ, EHB_GEMM_2CTA="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("M", [4, 8])
+def test_smaller_M_graphs(M):
+    """M below the reference default: level-0 rows are 2M wide; wave-of-one construction must still reproduce
+    the sequential oracle graph and the walk must match the oracle on it."""
+    n, d, nq = 1200, 24, 60
+    base, q = data(n, d, nq)
+    ix = ehb.NativeIndex(d, capacity=n, M=M, build_batch=1)
+    ix.add(base)
+    g = ix.export_graph()
+    o = orc.OracleHNSW(d, "l2", n, M=M)
+    o.add(base, threads=1)
+    og = o.export_graph()
+    assert np.array_equal(g["levels"], og["levels"])
+    rows = lambda l: [frozenset(int(x) for x in r if x != 0xFFFFFFFF) for r in l]
+    assert np.mean([a == b for a, b in zip(rows(g["links0"]), rows(og["links0"]))]) >= 0.99
+    ix.set_search_width(1)
+    l, dd, _ = ix.search(q, 5, ef=40)
+    ol, od, _ = o.search(q, 5, ef=40)
+    assert np.mean(l == ol) >= 0.99
+
+
+def test_large_ef_and_large_k():
+    """ef = 400 (16 entries per lane, one warp per query) with k = 300, and exact brute force at k = 1000."""
+    n, d, nq = 8000, 32, 40
+    base, q = data(n, d, nq)
+    ix = ehb.NativeIndex(d, capacity=n)
+    ix.add(base)
+    ix.build()
+    gt, gtd, _ = ix.search_bruteforce(q, 300)
+    l, dd, c = ix.search(q, 300, ef=400)
+    assert np.all(c == 300) and np.all(np.diff(dd, axis=1) >= 0)
+    assert all(len(set(r.tolist())) == 300 for r in l)
+    assert recall(l, gt) >= 0.9
+    ex, exd = orc.bruteforce(base, q[:8], 1000, "l2")
+    bl, bd, _ = ix.search_bruteforce(q[:8], 1000)
+    assert np.array_equal(bl, ex) and np.array_equal(bd.view(np.uint32), exd.view(np.uint32))
+    with pytest.raises(ehb.EhbError):
+        ix.search(q, 10, ef=513)                      # documented limit
