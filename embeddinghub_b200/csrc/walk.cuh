@@ -496,6 +496,18 @@ __device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, c
 
 // hnswlib searchBaseLayer(ST): best-first beam search with an ef-bounded
 // result set.  On return `u` holds the (<= ef) closest visited nodes (unordered).
+//
+// Why one array replaces hnswlib's two heaps (same expansion order, same result):
+//   hnswlib keeps `top_candidates` (max-heap, <= ef results) and `candidate_set` (min-heap of everything
+//   ever admitted).  A node enters both at the same moment (when top is not full or it beats the worst
+//   result) and is only ever removed from top by eviction of the worst.  The loop pops the closest
+//   unexpanded admitted node c and stops when dist(c) > worst result and top is full.  An admitted node
+//   that is no longer in top was evicted, i.e. is not closer than the current worst; every node still in
+//   top is.  Hence "closest unexpanded admitted node" is in top whenever top holds any unexpanded node, and
+//   when it does not, the pop would hit the stop condition (or the queue is empty).  So the walk is:
+//   repeatedly expand the closest entry of the result set whose expanded flag is clear, until none is
+//   left — which needs only the result set itself plus one flag per entry.  Admission is the same test
+//   (`cnt < ef || d < worst`); the tests check id-for-id equality with the oracle on identical graphs.
 // `exclude` (kInvalid = none) is never admitted (used when re-linking an updated
 // node).  The adjacency row of the likely next node (the closest unexpanded entry
 // before this hop's candidates are known) is requested ahead of the distance
