@@ -61,6 +61,10 @@ class ANNIndex:
     def set_ef(self, ef):
         self._nn.set_ef(ef)
 
+    def keys(self):
+        """Stored keys in insertion order (what Download streams, server.cc:212-233)."""
+        return list(self._key_to_label)
+
     def __len__(self):
         return self._next_label
 

@@ -224,7 +224,7 @@ class EmbeddingHubServicer:
             sp = self.hub._space(req.space)
         except HubError as e:
             self._fail(context, e)
-        for key in list(sp.index._key_to_label):
+        for key in sp.index.keys():
             yield M["DownloadResponse"](key=key, embedding=M["Embedding"](values=sp.index.get(key).tolist()))
 
 
