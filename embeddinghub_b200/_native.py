@@ -85,6 +85,7 @@ SYMBOLS = {
     "ehb_merge_topk_packed_dev": (C.c_int, [_U32, _U64, _U32, _VP, _U64, _VP, _VP, _VP, _I32, _VP]),
     "ehb_index_set_tuning": (C.c_int, [_VP, _U32, _U32, _U32, _U32]),
     "ehb_index_set_search_width": (C.c_int, [_VP, _U32]),
+    "ehb_index_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int64]),
 }
 
 _LIB = None
@@ -171,6 +172,9 @@ class NativeIndex:
 
     def set_tuning(self, stage_slots=0, stage_groups=0, hash_bits=0, warps_per_block=0):
         check(lib().ehb_index_set_tuning(self._h, stage_slots, stage_groups, hash_bits, warps_per_block))
+
+    def set_option(self, name, value):
+        check(lib().ehb_index_set_option(self._h, name.encode(), int(value)))
 
     def set_search_width(self, warps_per_query):
         check(lib().ehb_index_set_search_width(self._h, int(warps_per_query)))

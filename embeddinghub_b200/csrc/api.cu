@@ -126,6 +126,10 @@ struct ehb_index {
 
   // tuning (0 = auto)
   uint32_t t_slots = 0, t_groups = 0, t_hash_bits = 0, t_wpb = 0, t_team = 0;
+  // options (ehb_index_set_option)
+  uint32_t o_build_frac = 0;     // a wave links at most n_linked / build_frac points (0 = 64)
+  bool o_bf16_unfused = false;   // bf16 brute force: keep the distance tiles in HBM (A/B)
+  bool o_gemm_2cta = false;      // bf16 brute force: cta_group::2 cluster form of the fused GEMM
 
   ~ehb_index() {
     if (ev0) cudaEventDestroy(ev0);
@@ -388,7 +392,7 @@ struct ehb_index {
       }
       // a wave never exceeds 1/64 of the linked graph: points of one wave cannot see each other
       // (measured: recall within sampling noise of the sequential build from 1/32 on)
-      static const uint64_t frac = getenv("EHB_BUILD_FRAC") ? std::max(1, atoi(getenv("EHB_BUILD_FRAC"))) : 64;
+      const uint64_t frac = o_build_frac ? o_build_frac : 64;
       uint64_t b = std::min<uint64_t>(maxb, std::max<uint64_t>(1, n_linked / frac));
       b = std::min<uint64_t>(b, n - n_linked);
       ehb::BuildGraph bg = build_graph();
@@ -508,9 +512,9 @@ struct ehb_index {
       bctx.qnorm = q_norm2.p;
       bctx.xnorm = x_norm.p;
       bctx.kc = kc;
-      // fused selection state (EHB_BF16_UNFUSED=1 keeps the distance tiles in HBM: A/B switch)
-      static const bool unfused = getenv("EHB_BF16_UNFUSED") != nullptr;
-      bctx.fused = !unfused;
+      // fused selection state (option "bf16_unfused" keeps the distance tiles in HBM: A/B switch)
+      bctx.fused = !o_bf16_unfused;
+      bctx.variant = o_gemm_2cta ? 1 : 0;
       bctx.ccap = 2 * kc + 64;
       CU(bf_thr.grow(nq, 0, -1, s));
       CU(bf_cbuf.grow(nq * bctx.ccap, 0, -1, s));
@@ -738,6 +742,23 @@ int ehb_index_set_search_width(ehb_index* ix, uint32_t warps_per_query) {
   ENTER(ix);
   if (warps_per_query > 4) return fail(EHB_ERR_INVALID, "warps_per_query must be 0 (auto) or 1..4");
   ix->t_team = warps_per_query;
+  return EHB_OK;
+}
+
+int ehb_index_set_option(ehb_index* ix, const char* name, int64_t value) {
+  ENTER(ix);
+  if (!name) return fail(EHB_ERR_INVALID, "null option name");
+  const std::string o(name);
+  if (o == "build_frac") {
+    if (value < 0 || value > (1 << 20)) return fail(EHB_ERR_INVALID, "build_frac must be in 0..2^20");
+    ix->o_build_frac = (uint32_t)value;
+  } else if (o == "bf16_unfused") {
+    ix->o_bf16_unfused = value != 0;
+  } else if (o == "gemm_2cta") {
+    ix->o_gemm_2cta = value != 0;
+  } else {
+    return fail(EHB_ERR_INVALID, "unknown option: " + o);
+  }
   return EHB_OK;
 }
 

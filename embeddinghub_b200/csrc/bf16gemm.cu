@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(192, 1)
 // The leader CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256); both CTAs' TMA loads complete on the
 // leader's `full` barrier; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to both CTAs; the
 // non-leader's epilogue warps release the accumulator stage on the leader's `tmem_empty` barrier remotely.
-// Opt-in (EHB_GEMM_2CTA=1): measured on C4-shaped chunks it reaches 765 TFLOP/s in-kernel vs 826 TFLOP/s
+// Opt-in (ehb_index_set_option "gemm_2cta"): measured on C4-shaped chunks it reaches 765 TFLOP/s in-kernel vs 826 TFLOP/s
 // for the 1-CTA kernel — both sit on the L2 -> SM operand traffic (92 resp. 61 B/clk/SM requested against
 // a chip-wide LTS cap of ~6.3 KB/clk), so the next step is TMA multicast across a larger cluster, not this.
 // ---------------------------------------------------------------------------------------------------
@@ -527,7 +527,7 @@ __global__ void compact_candidates_kernel(uint64_t* __restrict__ run_keys, uint6
 cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* x_bf16, uint64_t x_rows, uint32_t dpad,
                                    int metric, const float* qnorm, const float* xnorm, uint64_t n_lo, uint64_t n_hi,
                                    float* thr, uint64_t* cbuf, uint32_t* ccount, uint32_t ccap, uint64_t* run_keys,
-                                   uint32_t kc, uint32_t* overflow, int sms, cudaStream_t s) {
+                                   uint32_t kc, uint32_t* overflow, int sms, int variant, cudaStream_t s) {
   if (dpad % GK != 0) return cudaErrorInvalidValue;
   CUtensorMap mq, mx;
   cudaError_t e;
@@ -536,7 +536,7 @@ cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* 
   e = cudaFuncSetAttribute(bf16_topk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
   if (e != cudaSuccess) return e;
   if (n_hi > n_lo) {
-    static const bool two_cta = getenv("EHB_GEMM_2CTA") != nullptr;
+    const bool two_cta = variant == 1;
     if (two_cta) {
       if ((e = make_map(&mx, x_bf16, x_rows, dpad, 128)) != cudaSuccess) return e;  // each CTA stages half a base tile
       e = cudaFuncSetAttribute(bf16_topk_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFused2Smem);

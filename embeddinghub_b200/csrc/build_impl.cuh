@@ -142,6 +142,116 @@ __global__ void __launch_bounds__(128) build_search_kernel(BuildGraph bg, WalkCf
   }
 }
 
+// hnswlib updatePoint, first half (the part before repairConnectionsForUpdate): when the vector of an
+// already linked point p changes, every one-hop neighbour nb of p (per layer) gets its adjacency row
+// re-selected by the heuristic over the closest ef_construction members of
+//   sCand = {p} U one-hop(p) U two-hop(p)   (minus nb itself),
+// distances measured from nb.  One warp per updated point; sCand (<= 1 + 2M + 2M*2M ids) is gathered
+// into `upd_cand` with the visited table deduplicating (a probe-budget overflow falls back to a linear
+// scan, so the set is exact).  Rows are written under a per-row spin lock (bb.row_fill, idle in this
+// phase) because two updated points of one wave may share a neighbour.
+constexpr uint32_t kUpdCandCap = 1088;  // >= 1 + 32 + 32*32
+
+template <int LPV, int NQ, int KPL>
+__global__ void __launch_bounds__(128) update_neighbors_kernel(BuildGraph bg, WalkCfg cfg,
+                                                               const uint32_t* __restrict__ ids, uint32_t b,
+                                                               BuildBuffers bb, uint32_t warp_smem) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GraphView& g = bg.g;
+  const uint32_t w = threadIdx.x >> 5;
+  const uint32_t pi = blockIdx.x * (blockDim.x >> 5) + w;
+  if (pi >= b) return;
+  const uint32_t p = ids[pi];
+  WarpCtx c;
+  ctx_init(c, smem + (size_t)w * warp_smem + 256, cfg, g.dpad);
+  Aux a = aux_of(c);
+  uint32_t* cand = bb.upd_cand + (size_t)pi * kUpdCandCap;
+  uint32_t* links0 = const_cast<uint32_t*>(g.links0);
+  uint32_t* links_up = const_cast<uint32_t*>(g.links_up);
+  const int level_p = min((int)bg.levels[p], g.max_level);
+  for (int layer = 0; layer <= level_p; ++layer) {
+    const uint32_t one = load_row(g, p, layer, c.lane);
+    const uint32_t n1 = __popc(__ballot_sync(0xffffffffu, one != kInvalid));
+    if (n1 == 0) continue;
+    // ---- sCand ----------------------------------------------------------------------------------
+    hash_clear(c);
+    uint32_t ncand = 0;
+    auto add_ids = [&](uint32_t id) {  // one id per lane (kInvalid = none; ids of one call are distinct)
+      uint32_t o = 0;
+      bool is_new = id != kInvalid && hash_insert(c, id, o);
+      __syncwarp();
+      if (__any_sync(0xffffffffu, o != 0)) {  // probe budget exhausted: decide by scanning what is stored
+        if (o)
+          for (uint32_t i = 0; i < ncand && is_new; ++i) is_new = cand[i] != id;
+        __syncwarp();
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, is_new);
+      if (is_new) cand[ncand + __popc(mask & lanemask_lt())] = id;
+      ncand += __popc(mask);
+      __syncwarp();
+    };
+    add_ids(c.lane == 0 ? p : kInvalid);
+    add_ids(one);
+    for (uint32_t j = 0; j < n1; ++j) {
+      const uint32_t e1 = __shfl_sync(0xffffffffu, one, j);
+      add_ids(load_row(g, e1, layer, c.lane));
+    }
+    // ---- re-select the row of every one-hop neighbour ----------------------------------------------
+    const uint32_t Mmax = layer == 0 ? g.M0 : g.M;
+    for (uint32_t j = 0; j < n1; ++j) {
+      const uint32_t nbid = __shfl_sync(0xffffffffu, one, j);
+      float4 qr[NQ];
+      load_vec_regs<LPV, NQ>(qr, g.vecs + (size_t)nbid * g.dpad, c.lane);
+      const uint32_t keep = min(bg.efc, ncand - 1u);  // nb is always a member of sCand
+      UList<KPL> u;
+      ul_clear<KPL>(u, keep, c.lane);
+      uint32_t cnt = 0, worst_hi = 0xFFFFFFFFu;
+      for (uint32_t b0 = 0; b0 < ncand; b0 += 32) {
+        uint32_t id = b0 + c.lane < ncand ? cand[b0 + c.lane] : kInvalid;
+        if (id == nbid) id = kInvalid;
+        uint32_t mask = __ballot_sync(0xffffffffu, id != kInvalid);
+        uint32_t m = __popc(mask);
+        if (!m) continue;
+        if (id != kInvalid) c.cand_id[__popc(mask & lanemask_lt())] = id;
+        __syncwarp();
+        eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
+        uint32_t myhi = 0xFFFFFFFFu, myid = kInvalid;
+        if (c.lane < m) myhi = f2ord(c.cand_dist[c.lane]), myid = c.cand_id[c.lane];
+        __syncwarp();
+        uint32_t qual = __ballot_sync(0xffffffffu, c.lane < m && (cnt < keep || myhi < worst_hi));
+        while (qual) {
+          int l = __ffs(qual) - 1;
+          qual &= qual - 1;
+          uint32_t hj = __shfl_sync(0xffffffffu, myhi, l);
+          uint32_t ij = __shfl_sync(0xffffffffu, myid, l);
+          if (cnt >= keep && hj >= worst_hi) continue;
+          ul_insert<KPL>(u, hj, ij, keep, cnt, worst_hi, c.lane);
+        }
+      }
+      c.cnt = 0;
+      for (;;) {
+        uint64_t key = ul_extract_min<KPL>(u, c.lane);
+        if (key == kMaxKey) break;
+        if (c.lane == 0) c.keys[c.cnt] = key;
+        c.cnt++;
+      }
+      __syncwarp();
+      const uint32_t nsel = heuristic_select<LPV, NQ>(c, g, Mmax, a);
+      const uint32_t rid = layer == 0 ? nbid : bg.cap + g.up_off[nbid] + (uint32_t)(layer - 1);
+      uint32_t* row = layer == 0 ? links0 + (size_t)nbid * g.M0
+                                 : links_up + (size_t)(g.up_off[nbid] + (uint32_t)(layer - 1)) * g.M;
+      if (c.lane == 0)
+        while (atomicCAS(&bb.row_fill[rid], 0u, 1u) != 0u) {
+        }
+      __syncwarp();
+      if (c.lane < Mmax) row[c.lane] = c.lane < nsel ? a.sel_id[c.lane] : kInvalid;
+      __threadfence();
+      __syncwarp();
+      if (c.lane == 0) atomicExch(&bb.row_fill[rid], 0u);
+    }
+  }
+}
+
 static __global__ void edge_count_kernel(BuildBuffers bb) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t n = min(*bb.edge_count, bb.edge_cap);
@@ -295,6 +405,19 @@ cudaError_t launch_build_t(const BuildGraph& bg, const WalkCfg& cfg, const uint3
   uint32_t ethreads = bb.edge_cap;
   auto ks = build_search_kernel<LPV, NQ, KPL>;
   auto km = merge_rows_kernel<LPV, NQ>;
+  if (is_update) {
+    // updatePoint's neighbour re-selection runs before the moved points are re-linked
+    if (!ids || !bb.upd_cand) return cudaErrorInvalidValue;
+    WalkCfg ucfg = cfg;
+    if (ucfg.hash_size < 4096) ucfg.hash_size = 4096;
+    uint32_t uwsm = build_warp_smem(ucfg, bg.g.dpad), uwpb = wpb;
+    while (uwpb > 1 && (size_t)uwsm * uwpb > 200 * 1024) uwpb >>= 1;
+    auto ku = update_neighbors_kernel<LPV, NQ, KPL>;
+    if ((e = cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)uwsm * uwpb))) !=
+        cudaSuccess)
+      return e;
+    ku<<<(b + uwpb - 1) / uwpb, 32 * uwpb, (size_t)uwsm * uwpb, s>>>(bg, ucfg, ids, b, bb, uwsm);
+  }
   if ((e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)) != cudaSuccess) return e;
   ks<<<grid, block, smem, s>>>(bg, cfg, ids, first, b, is_update ? 1 : 0, bb, wsm);

@@ -56,11 +56,12 @@ struct Bf16Ctx {
   uint32_t* overflow;   // device flag
   int sms;
   bool fused;
+  int variant;          // 0 = 1-CTA persistent kernel, 1 = cta_group::2 cluster form
 };
 cudaError_t launch_bf16_topk_chunk(const void* q_bf16, uint64_t nq, const void* x_bf16, uint64_t x_rows, uint32_t dpad,
                                    int metric, const float* qnorm, const float* xnorm, uint64_t n_lo, uint64_t n_hi,
                                    float* thr, uint64_t* cbuf, uint32_t* ccount, uint32_t ccap, uint64_t* run_keys,
-                                   uint32_t kc, uint32_t* overflow, int sms, cudaStream_t s);
+                                   uint32_t kc, uint32_t* overflow, int sms, int variant, cudaStream_t s);
 cudaError_t launch_to_bf16(const float* in, uint32_t in_stride, void* out_bf16, float* norms, uint64_t n, uint32_t dpad,
                            cudaStream_t s);
 cudaError_t launch_bf16_dist_tile(const void* q_bf16, uint64_t q_rows, const void* x_bf16, uint64_t x_rows,
@@ -97,6 +98,7 @@ struct BuildBuffers {
   uint32_t* seg_src;    // [edge_cap]
   float* seg_dist;      // [edge_cap]
   uint32_t* error_flag; // [1]
+  uint32_t* upd_cand;   // [batch][kUpdCandCap] sCand scratch of the update path (nullptr for plain inserts)
 };
 struct BuildGraph {
   GraphView g;          // links are written through these pointers (const-cast inside)

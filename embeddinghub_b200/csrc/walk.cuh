@@ -33,6 +33,7 @@ struct GraphView {
   const uint32_t* up_off;    // [n] first upper row of node i, kInvalid if level 0
   const uint32_t* links_up;  // [rows][M]
   const uint64_t* labels;    // [n]
+  const uint8_t* deleted;    // [n] tombstones (hnswlib markDelete), nullptr when the index has none
   uint32_t n, dim, dpad, M, M0, entry;
   int32_t max_level;
   int32_t metric;            // 0 = squared L2, 1 = 1 - dot (IP and cosine)
@@ -44,6 +45,7 @@ struct WalkCfg {
   uint32_t G;          // vectors per TMA staging group (<= 32), LPV = 32 only
   uint32_t NG;         // staging groups (ring depth, <= 8)
   uint32_t staged;     // 1 when the TMA staging ring is allocated
+  uint32_t dcap;       // capacity of the side queue of admitted-but-deleted candidates (0 = index has no tombstones)
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -64,6 +66,7 @@ __host__ __device__ inline uint32_t warp_smem_bytes(const WalkCfg& c, uint32_t d
   b += 128;  // cand_id[32]
   b += 128;  // cand_dist[32]
   b += 128;  // mbarriers (<= 8) + spare
+  b += align_up(c.dcap * 8u, 128);  // deleted-candidate queue: hi[dcap] | id[dcap]
   b += c.staged ? align_up(c.G * c.NG * dpad * 4u, 128) : 0u;
   return b;
 }
@@ -74,8 +77,10 @@ struct WarpCtx {
   uint32_t* cand_id;
   float* cand_dist;
   uint64_t* mbar;
+  uint32_t* dq_hi;   // deleted-candidate queue (unordered), see beam_search
+  uint32_t* dq_id;
   float* stage;
-  uint32_t lcap, hsize, G, NG, dpad, vbytes;
+  uint32_t lcap, hsize, G, NG, dpad, vbytes, dcap;
   uint32_t phases;  // one parity bit per staging group
   uint32_t cnt;     // live entries in keys[] (shared-memory list only)
   uint32_t lane;
@@ -100,6 +105,10 @@ __device__ __forceinline__ void ctx_init(WarpCtx& c, unsigned char* base, const 
   p += 128;
   c.mbar = (uint64_t*)p;
   p += 128;
+  c.dcap = cfg.dcap;
+  c.dq_hi = (uint32_t*)p;
+  c.dq_id = c.dq_hi + cfg.dcap;
+  p += align_up(cfg.dcap * 8u, 128);
   c.stage = (float*)p;
   c.phases = 0;
   c.cnt = 0;
@@ -373,6 +382,15 @@ __device__ __forceinline__ uint32_t ul_min_unexpanded(UList<KPL>& u, bool mark, 
   }
   return node;
 }
+// ordered distance of the closest unexpanded entry (0xFFFFFFFF when there is none)
+template <int KPL>
+__device__ __forceinline__ uint32_t ul_min_unexpanded_hi(const UList<KPL>& u) {
+  uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s)
+    if (!(u.id[s] & kExpandedFlag)) m = min(m, u.hi[s]);
+  return __reduce_min_sync(0xffffffffu, m);
+}
 template <int KPL>
 __device__ __forceinline__ bool ul_contains(const UList<KPL>& u, uint32_t id) {
   bool hit = false;
@@ -512,12 +530,45 @@ __device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, c
 // node).  The adjacency row of the likely next node (the closest unexpanded entry
 // before this hop's candidates are known) is requested ahead of the distance
 // evaluation, so its latency overlaps the vector loads.
+// Side queue of admitted-but-deleted candidates (only when g.deleted != nullptr).  hnswlib's
+// searchBaseLayerST<has_deletions=true> puts a tombstoned node into candidate_set (it is traversed) but never
+// into top_candidates (it is not a result and does not move lowerBound).  Such nodes cannot live in the
+// result set, so they wait here, unordered, until they are the closest unexpanded candidate.
+__device__ __forceinline__ void dq_push(WarpCtx& c, uint32_t& dn, uint32_t hi, uint32_t id, uint32_t& overflow) {
+  if (dn < c.dcap) {
+    if (c.lane == 0) c.dq_hi[dn] = hi, c.dq_id[dn] = id;
+    dn++;
+  } else {  // full: keep the closest dcap entries (the farthest is the least likely to be expanded)
+    uint32_t w = 0, wp = 0;
+    for (uint32_t i = c.lane; i < dn; i += 32)
+      if (c.dq_hi[i] >= w) w = c.dq_hi[i], wp = i;
+    uint32_t wm = __reduce_max_sync(0xffffffffu, w);
+    uint32_t b = __ballot_sync(0xffffffffu, w == wm);
+    uint32_t pos = __shfl_sync(0xffffffffu, wp, __ffs(b) - 1);
+    if (hi < wm && c.lane == 0) c.dq_hi[pos] = hi, c.dq_id[pos] = id;
+    overflow = 1;
+  }
+  __syncwarp();
+}
+// closest queued entry: returns its position (kInvalid when empty) and ordered distance
+__device__ __forceinline__ uint32_t dq_min(const WarpCtx& c, uint32_t dn, uint32_t& hi_out) {
+  uint32_t m = 0xFFFFFFFFu, mp = kInvalid;
+  for (uint32_t i = c.lane; i < dn; i += 32)
+    if (c.dq_hi[i] < m) m = c.dq_hi[i], mp = i;
+  uint32_t mm = __reduce_min_sync(0xffffffffu, m);
+  uint32_t b = __ballot_sync(0xffffffffu, m == mm && mp != kInvalid);
+  hi_out = mm;
+  return b ? __shfl_sync(0xffffffffu, mp, __ffs(b) - 1) : kInvalid;
+}
+
 template <int LPV, int NQ, int KPL, bool PREFETCH>
 __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], UList<KPL>& u,
                                             uint32_t ep, float epdist, int level, uint32_t ef, uint32_t exclude,
                                             WalkCounters& wc) {
   hash_clear(c);
   ul_clear<KPL>(u, ef, c.lane);
+  const uint8_t* __restrict__ del = c.dcap ? g.deleted : nullptr;  // warp-uniform
+  uint32_t dn = 0;                                                  // entries in the deleted-candidate queue
   uint32_t ovf = 0;
   if (c.lane == 0) {
     hash_insert(c, ep, ovf);
@@ -527,9 +578,11 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
   uint32_t cnt = 0;
   uint32_t worst_hi = 0xFFFFFFFFu;  // ordered distance of the worst entry once the set is full
   bool ovf_any = false;
-  if (ep != exclude) ul_insert<KPL>(u, f2ord(epdist), ep, ef, cnt, worst_hi, c.lane);
-  uint32_t node = ep;               // an excluded entry point is still expanded once
-  if (ep != exclude) node = ul_min_unexpanded<KPL>(u, true, c.lane);
+  // a tombstoned (or excluded) entry point is expanded once but never becomes a result
+  const bool ep_result = ep != exclude && !(del && del[ep]);
+  if (ep_result) ul_insert<KPL>(u, f2ord(epdist), ep, ef, cnt, worst_hi, c.lane);
+  uint32_t node = ep;
+  if (ep_result) node = ul_min_unexpanded<KPL>(u, true, c.lane);
   uint32_t nb = load_row(g, node, level, c.lane);
   for (;;) {
     if (level == 0) wc.hops_base++; else wc.hops_upper++;
@@ -557,18 +610,39 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       }
       uint32_t myhi = 0xFFFFFFFFu, myid = kInvalid;
       if (c.lane < m) myhi = f2ord(c.cand_dist[c.lane]), myid = c.cand_id[c.lane];
+      const bool mydel = del && c.lane < m && del[myid];
       __syncwarp();
       ovf_any = ovf_any || __any_sync(0xffffffffu, ovf);
       uint32_t qual = __ballot_sync(0xffffffffu, c.lane < m && (cnt < ef || myhi < worst_hi));
+      const uint32_t delmask = del ? __ballot_sync(0xffffffffu, mydel) : 0u;
       while (qual) {
         int j = __ffs(qual) - 1;
         qual &= qual - 1;
         uint32_t hj = __shfl_sync(0xffffffffu, myhi, j);
         uint32_t ij = __shfl_sync(0xffffffffu, myid, j);
         if (cnt >= ef && hj >= worst_hi) continue;
+        if ((delmask >> j) & 1u) {  // admitted like any candidate, but queued instead of becoming a result
+          dq_push(c, dn, hj, ij, ovf);
+          continue;
+        }
         if (ovf_any && ul_contains<KPL>(u, ij)) continue;
         ul_insert<KPL>(u, hj, ij, ef, cnt, worst_hi, c.lane);
         if (PREFETCH && c.lane == 0) prefetch_l2(g.links0 + (size_t)ij * g.M0);
+      }
+    }
+    if (dn) {
+      // candidate_set.top(): the closer of (closest unexpanded result, closest queued tombstone)
+      uint32_t dhi;
+      const uint32_t dpos = dq_min(c, dn, dhi);
+      if (dhi < ul_min_unexpanded_hi<KPL>(u)) {
+        if (cnt >= ef && dhi > worst_hi) break;  // hnswlib: dist > lowerBound && top_candidates.size() == ef
+        node = c.dq_id[dpos];
+        __syncwarp();
+        if (c.lane == 0) c.dq_hi[dpos] = c.dq_hi[dn - 1], c.dq_id[dpos] = c.dq_id[dn - 1];
+        dn--;
+        __syncwarp();
+        nb = load_row(g, node, level, c.lane);
+        continue;
       }
     }
     node = ul_min_unexpanded<KPL>(u, true, c.lane);

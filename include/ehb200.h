@@ -178,6 +178,13 @@ int ehb_index_set_search_width(ehb_index* ix, uint32_t warps_per_query);
 int ehb_index_set_tuning(ehb_index* ix, uint32_t stage_slots, uint32_t stage_groups, uint32_t hash_bits,
                          uint32_t warps_per_block);
 
+/* Named integer options (A/B switches and construction knobs that are not part of
+ * the reference's surface).  Unknown names fail with EHB_ERR_INVALID.
+ *   "build_frac"    a construction wave links at most size/build_frac points (0 = default 64)
+ *   "bf16_unfused"  bf16 brute force keeps the distance tiles in HBM (A/B of the fused epilogue)
+ *   "gemm_2cta"     bf16 brute force uses the cta_group::2 cluster form of the GEMM */
+int ehb_index_set_option(ehb_index* ix, const char* name, int64_t value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,9 @@
 //   InnerProductSpace / cosine     <- named by BASELINE.json north_star; cosine is
 //                                     hnswlib's Python convention (normalise + IP)
 //   BruteforceSearch               <- semantic oracle for the exact path
+//   markDelete / has_deletions     <- docs/reading_and_writing_embeddings.md:49-66 promises delete;
+//                                     upstream: tombstones are traversed but never returned, a re-added
+//                                     label is un-deleted and updated in place (addPoint)
 //
 // PINNING: checked against the reference's own known-answer tests
 // (embeddingstore/test/index_test.cc:17-60, sdk/python/test/offlinehub_test.py:63-86,
@@ -35,6 +38,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <queue>
@@ -142,6 +146,8 @@ struct Oracle {
   std::vector<float> vecs;                 // [cap][dim]
   std::vector<uint64_t> labels;            // [cap]
   std::vector<int> levels;                 // [cap]
+  std::vector<uint8_t> deleted;            // [cap] hnswlib DELETE_MARK
+  size_t num_deleted = 0;
   std::vector<uint32_t> links0;            // [cap][1+maxM0]  (count, ids...)
   std::vector<std::vector<uint32_t>> linksup;  // [cap] -> level*(1+maxM)
   std::unordered_map<uint64_t, idx_t> lookup;
@@ -159,6 +165,7 @@ struct Oracle {
     vecs.resize(cap * dim);
     labels.resize(cap);
     levels.assign(cap, 0);
+    deleted.assign(cap, 0);
     links0.assign(cap * (1 + maxM0), 0);
     linksup.resize(cap);
   }
@@ -195,6 +202,7 @@ struct Oracle {
     vecs.resize(new_cap * dim);
     labels.resize(new_cap);
     levels.resize(new_cap, 0);
+    deleted.resize(new_cap, 0);
     links0.resize(new_cap * (1 + maxM0), 0);
     linksup.resize(new_cap);
     std::vector<std::mutex>(new_cap).swap(node_locks);
@@ -214,9 +222,15 @@ struct Oracle {
     uint16_t* tags = vl->tag.data();
     uint16_t t = vl->cur;
     MaxHeap top, cand;
-    float lower = dist(q, vec(ep));
-    top.emplace(lower, ep);
-    cand.emplace(-lower, ep);
+    float lower;
+    if (!deleted[ep]) {
+      lower = dist(q, vec(ep));
+      top.emplace(lower, ep);
+      cand.emplace(-lower, ep);
+    } else {
+      lower = std::numeric_limits<float>::max();
+      cand.emplace(-lower, ep);
+    }
     tags[ep] = t;
     while (!cand.empty()) {
       DI cur = cand.top();
@@ -233,7 +247,7 @@ struct Oracle {
         float dd = dist(q, vec(nb));
         if (top.size() < efC || lower > dd) {
           cand.emplace(-dd, nb);
-          top.emplace(dd, nb);
+          if (!deleted[nb]) top.emplace(dd, nb);
           if (top.size() > efC) top.pop();
           if (!top.empty()) lower = top.top().first;
         }
@@ -425,6 +439,10 @@ struct Oracle {
       if (it != lookup.end()) {
         idx_t existing = it->second;
         lk.unlock();
+        if (deleted[existing]) {  // upstream addPoint: unmarkDeletedInternal, then updatePoint
+          deleted[existing] = 0;
+          num_deleted--;
+        }
         update_point(data, existing);
         return;
       }
@@ -483,14 +501,21 @@ struct Oracle {
     uint16_t* tags = vl->tag.data();
     uint16_t t = vl->cur;
     MaxHeap top, cand;
-    float lower = dist(q, vec(cur));
-    top.emplace(lower, cur);
-    cand.emplace(-lower, cur);
+    const bool has_del = num_deleted != 0;  // searchBaseLayerST<has_deletions>
+    float lower;
+    if (!has_del || !deleted[cur]) {
+      lower = dist(q, vec(cur));
+      top.emplace(lower, cur);
+      cand.emplace(-lower, cur);
+    } else {
+      lower = std::numeric_limits<float>::max();
+      cand.emplace(-lower, cur);
+    }
     tags[cur] = t;
     uint64_t hops = 0, evals = 0;
     while (!cand.empty()) {
       DI c = cand.top();
-      if (-c.first > lower && top.size() == efs) break;
+      if (-c.first > lower && (top.size() == efs || !has_del)) break;
       cand.pop();
       uint32_t* l = ll(c.second, 0);
       uint32_t sz = l[0];
@@ -503,7 +528,7 @@ struct Oracle {
         float dd = dist(q, vec(nb));
         if (top.size() < efs || lower > dd) {
           cand.emplace(-dd, nb);
-          top.emplace(dd, nb);
+          if (!has_del || !deleted[nb]) top.emplace(dd, nb);
           if (top.size() > efs) top.pop();
           if (!top.empty()) lower = top.top().first;
         }
@@ -636,10 +661,28 @@ void orc_metrics(void* h, uint64_t* hops_upper, uint64_t* hops0, uint64_t* evals
   if (reset) o->metric_hops_upper = 0, o->metric_hops = 0, o->metric_evals = 0;
 }
 
+// hnswlib markDelete(label): unknown label and double delete both throw.
+int orc_mark_delete(void* h, uint64_t label) {
+  Oracle* o = (Oracle*)h;
+  auto it = o->lookup.find(label);
+  if (it == o->lookup.end()) {
+    g_err = "Label not found";
+    return 1;
+  }
+  if (o->deleted[it->second]) {
+    g_err = "The requested to delete element is already deleted";
+    return 2;
+  }
+  o->deleted[it->second] = 1;
+  o->num_deleted++;
+  return 0;
+}
+uint64_t orc_deleted_count(void* h) { return ((Oracle*)h)->num_deleted; }
+
 int orc_get_vector(void* h, uint64_t label, float* out) {
   Oracle* o = (Oracle*)h;
   auto it = o->lookup.find(label);
-  if (it == o->lookup.end()) return 1;
+  if (it == o->lookup.end() || o->deleted[it->second]) return 1;  // getDataByLabel: "Label not found"
   std::memcpy(out, o->vec(it->second), o->dim * sizeof(float));
   return 0;
 }

@@ -45,6 +45,9 @@ def lib():
         L.orc_search.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int]
         L.orc_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_mark_delete.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_deleted_count.restype = C.c_uint64
+        L.orc_deleted_count.argtypes = [C.c_void_p]
         L.orc_get_vector.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_upper_rows.restype = C.c_uint64
         L.orc_upper_rows.argtypes = [C.c_void_p]
@@ -121,6 +124,18 @@ class OracleHNSW:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         lib().orc_metrics(self._h, C.byref(a), C.byref(b), C.byref(c), int(reset))
         return {"hops_upper": a.value, "hops0": b.value, "evals": c.value}
+
+    def mark_delete(self, label):
+        """hnswlib markDelete: KeyError for an unknown label, RuntimeError for a double delete."""
+        rc = lib().orc_mark_delete(self._h, int(label))
+        if rc == 1:
+            raise KeyError(label)
+        if rc:
+            raise RuntimeError(lib().orc_last_error().decode())
+
+    @property
+    def deleted_count(self):
+        return lib().orc_deleted_count(self._h)
 
     def get(self, label):
         out = np.empty(self.dim, dtype=np.float32)

@@ -418,8 +418,8 @@ def test_walk_edge_cases_empty_tiny_and_ragged():
 
 
 def test_bf16_bruteforce_two_cta_variant():
-    """The cta_group::2 (cluster of two SMs, M = 256) form of the fused GEMM is opt-in (EHB_GEMM_2CTA=1: it
-    measured no faster than the 1-CTA form this round); keep it correct."""
+    """The cta_group::2 (cluster of two SMs, M = 256) form of the fused GEMM is opt-in (option "gemm_2cta": it
+    measured no faster than the 1-CTA form); keep it correct."""
     import subprocess
     import sys
 
@@ -428,12 +428,12 @@ def test_bf16_bruteforce_two_cta_variant():
         "from embeddinghub_b200._native import BF16\n"
         "rng=np.random.default_rng(3); base=rng.standard_normal((60000,128),dtype=np.float32); q=rng.standard_normal((300,128),dtype=np.float32)\n"
         "for metric in ('ip','l2'):\n"
-        "    ix=ehb.NativeIndex(128,metric=metric,capacity=60000); ix.add(base)\n"
+        "    ix=ehb.NativeIndex(128,metric=metric,capacity=60000); ix.add(base); ix.set_option('gemm_2cta',1)\n"
         "    a=ix.search_bruteforce(q,10); b=ix.search_bruteforce(q,10,precision=BF16)\n"
         "    same=(a[0]==b[0]); assert same.mean()>=0.99, same.mean()\n"
         "    assert np.array_equal(a[1][same].view(np.uint32), b[1][same].view(np.uint32))\n"
         "print('ok')\n")
-    env = dict(os.environ, EHB_GEMM_2CTA="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
