@@ -5,9 +5,9 @@ DESIGN.md): a hand-written sm_100a CUDA library behind a C ABI
 (include/ehb200.h) plus the host-side mirrors of the reference's interfaces for
 that path.
 """
-from ._native import EhbError, NativeIndex, NO_LABEL, lib  # noqa: F401
+from ._native import EhbError, NativeIndex, NO_LABEL, ShardedIndex, lib  # noqa: F401
 from .ann_index import ANNIndex  # noqa: F401
 from .hub import EmbeddingHub, HubError  # noqa: F401
 from . import offline  # noqa: F401
 
-__all__ = ["ANNIndex", "EmbeddingHub", "HubError", "NativeIndex", "EhbError", "NO_LABEL", "lib", "offline"]
+__all__ = ["ANNIndex", "EmbeddingHub", "HubError", "NativeIndex", "ShardedIndex", "EhbError", "NO_LABEL", "lib", "offline"]

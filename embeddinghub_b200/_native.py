@@ -54,6 +54,11 @@ class Stats(C.Structure):
         ("max_level", C.c_uint32),
         ("entry_point", C.c_uint32),
         ("device_bytes", C.c_uint64),
+        ("deleted", C.c_uint64),
+        ("combined_batches", C.c_uint64),
+        ("combined_queries", C.c_uint64),
+        ("metric", C.c_uint32),
+        ("reserved_", C.c_uint32),
     ]
 
 
@@ -68,6 +73,7 @@ SYMBOLS = {
     "ehb_index_add": (C.c_int, [_VP, _U64, _VP, _VP]),
     "ehb_index_add_dev": (C.c_int, [_VP, _U64, _VP, _VP]),
     "ehb_index_build": (C.c_int, [_VP]),
+    "ehb_index_remove": (C.c_int, [_VP, _U64, _VP]),
     "ehb_index_set_ef": (C.c_int, [_VP, _U32]),
     "ehb_index_size": (C.c_int, [_VP, C.POINTER(_U64)]),
     "ehb_index_get": (C.c_int, [_VP, _U64, _VP]),
@@ -86,6 +92,26 @@ SYMBOLS = {
     "ehb_index_set_tuning": (C.c_int, [_VP, _U32, _U32, _U32, _U32]),
     "ehb_index_set_search_width": (C.c_int, [_VP, _U32]),
     "ehb_index_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int64]),
+    "ehb_sharded_create": (C.c_int, [C.POINTER(Params), C.POINTER(_I32), _U32, _U64, C.POINTER(_VP)]),
+    "ehb_sharded_destroy": (C.c_int, [_VP]),
+    "ehb_sharded_n_shards": (C.c_int, [_VP, C.POINTER(_U32)]),
+    "ehb_sharded_shard": (C.c_int, [_VP, _U32, C.POINTER(_VP)]),
+    "ehb_sharded_add": (C.c_int, [_VP, _U64, _VP, _VP]),
+    "ehb_sharded_remove": (C.c_int, [_VP, _U64, _VP]),
+    "ehb_sharded_get": (C.c_int, [_VP, _U64, _VP]),
+    "ehb_sharded_size": (C.c_int, [_VP, C.POINTER(_U64)]),
+    "ehb_sharded_build": (C.c_int, [_VP]),
+    "ehb_sharded_set_ef": (C.c_int, [_VP, _U32]),
+    "ehb_sharded_search": (C.c_int, [_VP, _U64, _VP, _U32, _U32, _VP, _VP, _VP]),
+    "ehb_sharded_search_bruteforce": (C.c_int, [_VP, _U64, _VP, _U32, C.c_int, _VP, _VP, _VP]),
+    "ehb_exchange_create": (C.c_int, [_I32, _U32, _U32, _U64, _U32, C.POINTER(_VP)]),
+    "ehb_exchange_destroy": (C.c_int, [_VP]),
+    "ehb_exchange_ipc_handle": (C.c_int, [_VP, _VP]),
+    "ehb_exchange_open": (C.c_int, [_VP, _VP]),
+    "ehb_exchange_attach_local": (C.c_int, [_VP, _U32, _VP]),
+    "ehb_exchange_begin": (C.c_int, [_VP, _U64, _U32, C.POINTER(_VP), C.POINTER(_VP)]),
+    "ehb_exchange_merge_dev": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "ehb_exchange_timed_out": (C.c_int, [_VP, C.POINTER(_U32)]),
 }
 
 _LIB = None
@@ -143,7 +169,8 @@ class NativeIndex:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().ehb_index_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().ehb_index_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -166,6 +193,14 @@ class NativeIndex:
 
     def build(self):
         check(lib().ehb_index_build(self._h))
+
+    def remove(self, labels):
+        """Tombstones (hnswlib markDelete): KeyError for an unknown label."""
+        lab = np.ascontiguousarray(np.atleast_1d(labels), dtype=np.uint64)
+        rc = lib().ehb_index_remove(self._h, lab.shape[0], _p(lab))
+        if rc == 5:
+            raise KeyError(labels)
+        check(rc)
 
     def set_ef(self, ef):
         check(lib().ehb_index_set_ef(self._h, int(ef)))
@@ -279,5 +314,84 @@ class NativeIndex:
         ix._h = h
         st = Stats()
         check(lib().ehb_index_stats(h, C.byref(st)))
-        ix.dim, ix.M, ix.metric = st.dim, st.M, None
+        ix.dim, ix.M, ix.metric = st.dim, st.M, {v: k for k, v in METRICS.items()}[st.metric]
         return ix
+
+
+class ShardedIndex:
+    """ehb_sharded: one process, several GPUs of one box, behind the same host entry points."""
+
+    def __init__(self, dim, devices, metric="l2", capacity=128, M=16, ef_construction=200, ef_search=10, seed=100,
+                 shard_span=0, build_batch=0):
+        L = lib()
+        self.dim, self.metric, self.M = int(dim), metric, int(M)
+        p = Params()
+        L.ehb_params_default(C.byref(p), self.dim)
+        p.metric, p.capacity, p.M = METRICS[metric], int(capacity), int(M)
+        p.ef_construction, p.ef_search, p.seed, p.build_batch = int(ef_construction), int(ef_search), int(seed), int(build_batch)
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        check(L.ehb_sharded_create(C.byref(p), devs, len(devices), int(shard_span), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ehb_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, vecs, labels=None):
+        v = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
+        lab = None if labels is None else np.ascontiguousarray(labels, dtype=np.uint64)
+        check(lib().ehb_sharded_add(self._h, v.shape[0], _p(v), _p(lab)))
+
+    def remove(self, labels):
+        lab = np.ascontiguousarray(np.atleast_1d(labels), dtype=np.uint64)
+        rc = lib().ehb_sharded_remove(self._h, lab.shape[0], _p(lab))
+        if rc == 5:
+            raise KeyError(labels)
+        check(rc)
+
+    def build(self):
+        check(lib().ehb_sharded_build(self._h))
+
+    def get(self, label):
+        out = np.empty(self.dim, np.float32)
+        rc = lib().ehb_sharded_get(self._h, int(label), _p(out))
+        if rc == 5:
+            raise KeyError(label)
+        check(rc)
+        return out
+
+    @property
+    def size(self):
+        n = C.c_uint64()
+        check(lib().ehb_sharded_size(self._h, C.byref(n)))
+        return n.value
+
+    def shard(self, i):
+        h = C.c_void_p()
+        check(lib().ehb_sharded_shard(self._h, i, C.byref(h)))
+        ix = NativeIndex.__new__(NativeIndex)
+        ix._h, ix.dim, ix.M, ix.metric = h, self.dim, self.M, self.metric
+        ix._owned = False   # borrowed: the sharded index destroys it
+        return ix
+
+    def search(self, q, k, ef=0):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        labels, dists, counts = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32), np.zeros(nq, np.uint32)
+        check(lib().ehb_sharded_search(self._h, nq, _p(q), k, ef, _p(labels), _p(dists), _p(counts)))
+        return labels, dists, counts
+
+    def search_bruteforce(self, q, k, precision=FP32):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        labels, dists, counts = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32), np.zeros(nq, np.uint32)
+        check(lib().ehb_sharded_search_bruteforce(self._h, nq, _p(q), k, precision, _p(labels), _p(dists), _p(counts)))
+        return labels, dists, counts

@@ -9,6 +9,7 @@
 // (oracle/hnsw_oracle.cpp: canon_l2 / canon_dot) restates on the CPU, so ids
 // are comparable bit-for-bit under the total order (distance asc, index asc).
 #include "kernels.h"
+#include "merge.cuh"
 
 namespace ehb {
 
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(256) bf_dist_kernel(const float* __restrict__ 
 // dropped before they cost an insert.
 __global__ void bf_select_kernel(const float* __restrict__ dist, uint64_t nc, uint64_t nn, uint64_t n0, uint64_t qn,
                                  uint32_t slices, uint32_t k, uint64_t* __restrict__ part_keys,
-                                 const uint64_t* __restrict__ run_keys, uint64_t q0) {
+                                 const uint64_t* __restrict__ run_keys, uint64_t q0,
+                                 const uint8_t* __restrict__ deleted) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const uint64_t job = (uint64_t)blockIdx.x * wpb + w;
@@ -92,9 +94,9 @@ __global__ void bf_select_kernel(const float* __restrict__ dist, uint64_t nc, ui
   for (uint64_t i0 = lo; i0 < hi; i0 += 32) {
     uint64_t i = i0 + c.lane;
     uint64_t key = kMaxKey;
-    if (i < hi) key = make_key(row[i], (uint32_t)(n0 + i));
+    if (i < hi && !(deleted && deleted[n0 + i])) key = make_key(row[i], (uint32_t)(n0 + i));
     uint32_t worst_hi = c.cnt >= k ? key_hi(c.keys[k - 1]) : 0xFFFFFFFFu;
-    uint32_t qual = __ballot_sync(0xffffffffu, i < hi && key < thr && (c.cnt < k || key_hi(key) < worst_hi));
+    uint32_t qual = __ballot_sync(0xffffffffu, key != kMaxKey && key < thr && (c.cnt < k || key_hi(key) < worst_hi));
     while (qual) {
       int j = __ffs(qual) - 1;
       qual &= qual - 1;
@@ -225,7 +227,7 @@ cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, ui
         if (slices == 0) slices = 1;
         uint64_t jobs = qn * slices;
         bf_select_kernel<<<(unsigned)((jobs + wpb - 1) / wpb), 32 * wpb, smem, s>>>(
-            sc.dist, sc.nc, nn, n0, qn, slices, ksel, sc.part_keys, sc.run_keys, q0);
+            sc.dist, sc.nc, nn, n0, qn, slices, ksel, sc.part_keys, sc.run_keys, q0, sc.deleted);
         bf_merge_kernel<<<(unsigned)((qn + wpb - 1) / wpb), 32 * wpb, smem, s>>>(sc.run_keys, sc.part_keys, q0, qn,
                                                                                 slices, ksel);
       }
@@ -277,52 +279,14 @@ cudaError_t launch_bruteforce(const float* vecs, uint32_t dpad, uint32_t dim, ui
 // K4: per query, G sorted lists of (dist, label) -> global top-k.  One warp per
 // query, lane g walks list g; each step a warp arg-min on (distance, label).
 // ---------------------------------------------------------------------------
-// rank g's lists start at (bytes) dists + g * stride_d and labels + g * stride_l, so separate [G][nq][k]
-// arrays and one packed all-gather buffer [G][labels | dists] are both merged in place.
+// (device part: merge.cuh)
 __global__ void merge_topk_kernel(uint32_t G, uint64_t nq, uint32_t k, const float* __restrict__ dists,
                                   const uint64_t* __restrict__ labels, uint64_t stride_d, uint64_t stride_l,
                                   float* __restrict__ out_dists, uint64_t* __restrict__ out_labels,
                                   uint32_t* __restrict__ out_counts) {
   uint64_t q = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  uint32_t lane = threadIdx.x & 31;
   if (q >= nq) return;
-  uint32_t head = 0;
-  const uint32_t g = lane < G ? lane : 0;
-  const float* dl = (const float*)((const unsigned char*)dists + (uint64_t)g * stride_d) + q * k;
-  const uint64_t* ll = (const uint64_t*)((const unsigned char*)labels + (uint64_t)g * stride_l) + q * k;
-  uint32_t found = 0;
-  for (uint32_t i = 0; i < k; ++i) {
-    uint32_t od = 0xFFFFFFFFu;
-    uint64_t lab = 0xFFFFFFFFFFFFFFFFull;
-    if (lane < G && head < k) {
-      lab = ll[head];
-      if (lab != 0xFFFFFFFFFFFFFFFFull) od = f2ord(dl[head]);
-    }
-    uint32_t bd = od, bl = lane;
-    uint64_t blab = lab;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      uint32_t xd = __shfl_xor_sync(0xffffffffu, bd, o);
-      uint64_t xl = __shfl_xor_sync(0xffffffffu, blab, o);
-      uint32_t xn = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (xd < bd || (xd == bd && (xl < blab || (xl == blab && xn < bl)))) bd = xd, blab = xl, bl = xn;
-    }
-    bool ok = blab != 0xFFFFFFFFFFFFFFFFull;
-    if (lane == 0) {
-      out_labels[q * k + i] = ok ? blab : 0xFFFFFFFFFFFFFFFFull;
-      if (out_dists) out_dists[q * k + i] = ok ? ord2f(bd) : INFINITY;
-    }
-    if (!ok) {
-      for (uint32_t j = i + 1 + lane; j < k; j += 32) {
-        out_labels[q * k + j] = 0xFFFFFFFFFFFFFFFFull;
-        if (out_dists) out_dists[q * k + j] = INFINITY;
-      }
-      break;
-    }
-    found++;
-    if (lane == bl) head++;
-  }
-  if (lane == 0 && out_counts) out_counts[q] = found;
+  merge_one_query(G, q, threadIdx.x & 31, k, dists, labels, stride_d, stride_l, out_dists, out_labels, out_counts);
 }
 
 cudaError_t launch_merge_topk(uint32_t G, uint64_t nq, uint32_t k, const float* dists, const uint64_t* labels,

@@ -150,8 +150,6 @@ __global__ void __launch_bounds__(128) build_search_kernel(BuildGraph bg, WalkCf
 // into `upd_cand` with the visited table deduplicating (a probe-budget overflow falls back to a linear
 // scan, so the set is exact).  Rows are written under a per-row spin lock (bb.row_fill, idle in this
 // phase) because two updated points of one wave may share a neighbour.
-constexpr uint32_t kUpdCandCap = 1088;  // >= 1 + 32 + 32*32
-
 template <int LPV, int NQ, int KPL>
 __global__ void __launch_bounds__(128) update_neighbors_kernel(BuildGraph bg, WalkCfg cfg,
                                                                const uint32_t* __restrict__ ids, uint32_t b,

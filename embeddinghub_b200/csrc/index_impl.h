@@ -35,6 +35,8 @@
 namespace ehb {
 
 int fail(int code, const std::string& msg);  // sets the thread-local error text, returns code
+const std::string& last_error_text();
+extern thread_local std::string g_err;
 
 #define CU(expr)                                                                                         \
   do {                                                                                                   \

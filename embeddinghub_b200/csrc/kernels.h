@@ -9,6 +9,7 @@ namespace ehb {
 
 constexpr uint32_t kMaxDim = 2048;  // pad_dim() supports rows up to 2048 floats
 constexpr uint32_t kMaxEf = 512;    // register-resident list: 16 keys per lane
+constexpr uint32_t kUpdCandCap = 1088;  // update path: sCand capacity per moved point, >= 1 + 32 + 32*32
 
 // K2 — batched k-NN graph walk (hnswlib searchKnn).  ef >= k, cfg.lcap >= ef.
 // stats: [nq][4] u32 = hops_upper, hops_base, evals, overflow.
@@ -35,6 +36,7 @@ struct BruteScratch {
   uint64_t* part_keys;  // [qb][slices][k]
   uint64_t* run_keys;   // [nq][k] running best
   uint64_t qb, nc, slices;
+  const uint8_t* deleted = nullptr;  // tombstones: such rows never form a key
 };
 cudaError_t launch_bruteforce_exact(const float* vecs, uint32_t dpad, uint32_t dim, uint64_t n, const uint64_t* labels,
                                     int metric, const float* queries /*[nq][dim]*/, uint64_t nq, uint32_t k,

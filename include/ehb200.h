@@ -15,8 +15,13 @@
  *     synchronise, for callers that keep queries/results resident in HBM.
  *   - results are nearest-first; rows with fewer than k hits are padded with
  *     EHB_NO_LABEL / +inf and the true count is written to out_counts.
- *   - searches on one index may be issued from several host threads (they are
- *     serialised per index); mutations are exclusive.
+ *   - searches are re-entrant: several host threads may search one index at the
+ *     same time (each in-flight search has its own stream and scratch; concurrent
+ *     small ehb_index_search calls are coalesced into one batched launch by a
+ *     combining queue — the goroutine-per-request pattern of
+ *     serving/serving.go:744-771); mutations (add / remove / build / import) are
+ *     exclusive.  The reference serialises everything under one service mutex
+ *     (embeddinghub/embeddingstore/server.cc:175).
  *   - there is no CPU fallback: every call fails with EHB_ERR_CUDA when no
  *     sm_100-class device is usable.
  */
@@ -83,6 +88,11 @@ typedef struct ehb_stats {
   uint64_t size, capacity, upper_rows;
   uint32_t dim, M, max_level, entry_point;
   uint64_t device_bytes;
+  uint64_t deleted;           /* tombstones (ehb_index_remove); `size` counts them, like hnswlib   */
+  uint64_t combined_batches;  /* batched launches issued by the combining queue of ehb_index_search */
+  uint64_t combined_queries;  /* queries those launches carried                                     */
+  uint32_t metric;            /* ehb_metric of the index                                            */
+  uint32_t reserved_;
 } ehb_stats;
 
 const char* ehb_last_error(void);
@@ -103,6 +113,13 @@ int ehb_index_destroy(ehb_index* ix);
 int ehb_index_add(ehb_index* ix, uint64_t n, const float* vecs_host, const uint64_t* labels_host);
 int ehb_index_add_dev(ehb_index* ix, uint64_t n, const float* vecs_dev, const uint64_t* labels_host);
 int ehb_index_build(ehb_index* ix);
+
+/* Delete (embeddinghub/docs/reading_and_writing_embeddings.md:49-66 promises delete / multidelete; hnswlib
+ * markDelete semantics): the points stay in the graph as tombstones — traversed by searches, never returned,
+ * ehb_index_get answers EHB_ERR_NOT_FOUND, size() still counts them.  Unknown label: EHB_ERR_NOT_FOUND;
+ * already deleted: EHB_ERR_STATE.  Adding a deleted label again un-deletes it and updates it in place
+ * (hnswlib addPoint). */
+int ehb_index_remove(ehb_index* ix, uint64_t n, const uint64_t* labels_host);
 
 /* hnswlib setEf (never called by the reference; named by BASELINE configs). */
 int ehb_index_set_ef(ehb_index* ix, uint32_t ef);
@@ -178,11 +195,55 @@ int ehb_index_set_search_width(ehb_index* ix, uint32_t warps_per_query);
 int ehb_index_set_tuning(ehb_index* ix, uint32_t stage_slots, uint32_t stage_groups, uint32_t hash_bits,
                          uint32_t warps_per_block);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Range-sharded index over several GPUs of one box (SURVEY.md §8b B4 "device_ids[], n_dev"; §8e).
+ * One process drives n_dev devices: labels [i*span, (i+1)*span) live on shard i % n_dev (span 0: label %
+ * n_dev); every shard owns an independent graph; a search runs on every shard, whose kernels store their
+ * top-k straight into device_ids[0]'s gather buffer over NVLink (peer access), and one merge kernel there
+ * produces the result.  No collective on either path.  Same conventions as the single-index calls. */
+typedef struct ehb_sharded ehb_sharded; /* opaque */
+int ehb_sharded_create(const ehb_params* p /* device ignored; capacity per shard */, const int32_t* device_ids,
+                       uint32_t n_dev, uint64_t shard_span, ehb_sharded** out);
+int ehb_sharded_destroy(ehb_sharded* sh);
+int ehb_sharded_n_shards(ehb_sharded* sh, uint32_t* out);
+int ehb_sharded_shard(ehb_sharded* sh, uint32_t i, ehb_index** out /* borrowed */);
+int ehb_sharded_add(ehb_sharded* sh, uint64_t n, const float* vecs_host, const uint64_t* labels_host);
+int ehb_sharded_remove(ehb_sharded* sh, uint64_t n, const uint64_t* labels_host);
+int ehb_sharded_get(ehb_sharded* sh, uint64_t label, float* out_vec_host);
+int ehb_sharded_size(ehb_sharded* sh, uint64_t* out);
+int ehb_sharded_build(ehb_sharded* sh); /* shards build concurrently */
+int ehb_sharded_set_ef(ehb_sharded* sh, uint32_t ef);
+int ehb_sharded_search(ehb_sharded* sh, uint64_t nq, const float* queries_host, uint32_t k, uint32_t ef,
+                       uint64_t* out_labels_host, float* out_dists_host, uint32_t* out_counts_host);
+int ehb_sharded_search_bruteforce(ehb_sharded* sh, uint64_t nq, const float* queries_host, uint32_t k, int precision,
+                                  uint64_t* out_labels_host, float* out_dists_host, uint32_t* out_counts_host);
+
+/* Shard exchange for one-process-per-GPU deployments (torchrun / MPI): replaces "one ncclAllGather of the
+ * per-shard top-k + merge kernel"  with ONE kernel per rank that pushes this rank's lists
+ * into every peer's receive buffer with stores over NVLink (CUDA IPC mappings), flags them per slice and
+ * merges each slice as soon as all peers' flags are up.  Protocol per rank:
+ *   create -> ipc_handle -> (exchange the 64-byte handles out of band, e.g. one torch.distributed
+ *   all_gather at start-up) -> open;  then per step, in lock step on every rank:
+ *   begin(nq, k) -> run the local search with the returned output pointers -> merge_dev(stream). */
+#define EHB_IPC_HANDLE_BYTES 64
+typedef struct ehb_exchange ehb_exchange; /* opaque */
+int ehb_exchange_create(int32_t device, uint32_t world, uint32_t rank, uint64_t max_nq, uint32_t max_k,
+                        ehb_exchange** out);
+int ehb_exchange_destroy(ehb_exchange* ex);
+int ehb_exchange_ipc_handle(ehb_exchange* ex, void* out_handle /* EHB_IPC_HANDLE_BYTES */);
+int ehb_exchange_open(ehb_exchange* ex, const void* handles /* [world][EHB_IPC_HANDLE_BYTES], rank order */);
+int ehb_exchange_attach_local(ehb_exchange* ex, uint32_t peer_rank, ehb_exchange* peer /* same process */);
+int ehb_exchange_begin(ehb_exchange* ex, uint64_t nq, uint32_t k, uint64_t** labels_dev, float** dists_dev);
+int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev,
+                           void* stream);
+int ehb_exchange_timed_out(ehb_exchange* ex, uint32_t* out /* 1: a wait for a peer gave up (~20 s) */);
+
 /* Named integer options (A/B switches and construction knobs that are not part of
  * the reference's surface).  Unknown names fail with EHB_ERR_INVALID.
  *   "build_frac"    a construction wave links at most size/build_frac points (0 = default 64)
  *   "bf16_unfused"  bf16 brute force keeps the distance tiles in HBM (A/B of the fused epilogue)
- *   "gemm_2cta"     bf16 brute force uses the cta_group::2 cluster form of the GEMM */
+ *   "gemm_2cta"     bf16 brute force uses the cta_group::2 cluster form of the GEMM
+ *   "combine"       1 (default): concurrent host searches of <= 256 queries share batched launches */
 int ehb_index_set_option(ehb_index* ix, const char* name, int64_t value);
 
 #ifdef __cplusplus

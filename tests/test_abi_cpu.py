@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert set(names) == set(_native.SYMBOLS), set(names) ^ set(_native.SYMBOLS)
-    assert ehb.lib().ehb_abi_version() == 1
+    assert ehb.lib().ehb_abi_version() == 2
 
 
 def test_params_default_match_reference_defaults():
