@@ -1,27 +1,38 @@
 #!/usr/bin/env python
-"""ehb200 benchmark — batched k-NN over the HNSW graph (BASELINE.json configs[1], "C2").
+"""ehb200 benchmark — batched k-NN over the HNSW graph at the north-star configurations.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ehb200|reference] [--workload c2|c3s|...]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ehb200|reference] [--workload auto|c2|c3|...]
 
-A step = one pass of the hot path over one batch of Q synthetic queries.
-  value      queries/s, index and queries resident in HBM (ehb_index_search_dev), device-timed
-  e2e        queries/s through the host C-ABI entry point (ehb_index_search): pinned host
-             queries -> H2D -> walk -> D2H labels/distances/counts, all inside the timed region
-  roofline   algorithmic bytes of the walk kernel (hnswlib hop / distance-evaluation counters,
-             SURVEY.md §8d) / its CUDA-event duration, against the measured HBM copy bandwidth
-  cpu_baseline  the CPU oracle (hnswlib restatement) searching the SAME graph and queries on the
-             host cores of this box (rank 0, N=1 only)
---impl reference times the oracle end to end on the host cores (its own CPU-built graph).
+Default workload ("auto"): ONE GPU -> BASELINE.json configs[2] (C3: N=10M d=768 Q=10k k=10 ef=128 InnerProduct,
+the north-star target, 30.7 GB of vectors on one B200); N > 1 GPUs -> configs[4] (C5: d=128 Q=10k k=100 ef=256
+cosine, range-sharded, 12.5M points per GPU = 100M at 8 GPUs).  A step = one pass of the hot path over one
+batch of Q synthetic queries.
+  value        queries/s over the WHOLE index (Q / step time), index and queries resident in HBM, device-timed
+               with CUDA events on the launch stream, L2 flushed between steps, max over ranks
+  e2e          the same through the host entry point (ehb_index_search): pinned host queries -> H2D -> walk ->
+               D2H of labels / distances / counts, all inside the timed region
+  roofline     algorithmic bytes of the walk kernel (hnswlib hop / distance-evaluation counters of that very
+               launch) / its CUDA-event duration, against the measured HBM copy bandwidth
+  cpu_baseline the CPU oracle (hnswlib restatement) walking the SAME graph with the SAME queries on the host
+               cores of this box: threads pinned one per CPU, best and median of 5 passes (rank 0, N=1 only)
+  parity       at a stated sub-sample N' of the same data: recall@k of the oracle on its OWN CPU-built graph
+               (= the reference's behaviour), of the GPU-built graph walked by the GPU, and of the GPU-built
+               graph walked by the oracle, all at the same ef, against exact ground truth
+--impl reference times the oracle end to end on the host cores (its own CPU-built graph over a time-bounded
+prefix of the same base set).
 
-Multi-GPU (torchrun, one rank per GPU): the index is range-sharded, every rank searches all Q
-queries over its own shard, one NCCL all-gather of the per-shard top-k, one merge kernel.
-Weak scaling: the shard size per GPU is fixed, so the whole-job aggregate is G*Q shard-level
-k-NN searches per step; `global_queries_per_s` (Q / step time) is reported next to it.
+Multi-GPU (torchrun, one rank per GPU): the index is range-sharded, every rank searches all Q queries over its
+own shard, the per-shard top-k lists meet in ONE exchange step (default: the library's peer-memory exchange —
+one push + flag + merge kernel per rank over NVLink, no collective; --exchange nccl: one ncclAllGather + merge
+kernel).  Weak scaling: the shard size per GPU is fixed, so the index grows with N; `value` stays Q / step
+time (queries answered over N_total points) and `shard_searches_per_s` = N x that is the aggregate of
+shard-level searches.
 """
 import argparse
 import ctypes as C
 import json
 import os
+import platform
 import subprocess
 import sys
 import threading
@@ -54,22 +65,51 @@ WORKLOADS = {
                desc="brute-force N=10M d=768 Q=4096 k=100 bf16 tensor-core GEMM path (BASELINE.json configs[3])"),
 }
 BASE_SEED, QUERY_SEED = 1234, 4321
-
+CHUNK = 1 << 20                     # rows per generated chunk (chunks of 1M rows)
 
 DIST = "gaussian"   # --dist gmm: report-only secondary distribution: 1024-centre GMM, sigma 0.3
 
 
-def gen(n, d, seed):
+def gen_chunks(n, d, seed):
+    """Yields (first_row, rows[<=1M][d]) of the prescribed stream: numpy default_rng(seed) (PCG64)
+    standard_normal float32, generated in chunks of 1M rows; a prefix of the stream is the same data."""
     rng = np.random.default_rng(seed)
-    out = np.empty((n, d), np.float32)
     centres = np.random.default_rng(99).standard_normal((1024, d), dtype=np.float32) if DIST == "gmm" else None
-    for i in range(0, n, 1 << 20):
-        m = min(1 << 20, n - i)
-        out[i:i + m] = rng.standard_normal((m, d), dtype=np.float32)
+    for i in range(0, n, CHUNK):
+        m = min(CHUNK, n - i)
+        x = rng.standard_normal((m, d), dtype=np.float32)
         if centres is not None:
-            out[i:i + m] *= np.float32(0.3)
-            out[i:i + m] += centres[rng.integers(0, 1024, m)]
+            x *= np.float32(0.3)
+            x += centres[rng.integers(0, 1024, m)]
+        yield i, x
+
+
+def gen(n, d, seed):
+    out = np.empty((n, d), np.float32)
+    for i, x in gen_chunks(n, d, seed):
+        out[i:i + x.shape[0]] = x
     return out
+
+
+def prefetched(it, depth=2):
+    """Runs a generator in a background thread (numpy releases the GIL while filling)."""
+    import queue
+
+    qu, end = queue.Queue(maxsize=depth), object()
+
+    def run():
+        try:
+            for item in it:
+                qu.put(item)
+        finally:
+            qu.put(end)
+
+    threading.Thread(target=run, daemon=True).start()
+    while True:
+        item = qu.get()
+        if item is end:
+            return
+        yield item
 
 
 def recall_at_k(found, truth):
@@ -127,60 +167,154 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def host_cores():
+def host_cpus():
     try:
-        return len(os.sched_getaffinity(0))
+        return sorted(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        return list(range(os.cpu_count() or 1))
+
+
+def host_info():
+    model = platform.processor() or ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    load = None
+    try:
+        load = os.getloadavg()[0]
+    except Exception:
+        pass
+    return {"cpu_model": model, "nproc": len(host_cpus()), "loadavg_1m_before": load}
+
+
+def timed_passes(fn, passes=5, min_passes=3, budget_s=30.0):
+    """Best and median wall time of repeated passes (perf_counter), bounded by a time budget."""
+    fn()  # warm
+    ts, t_all = [], time.perf_counter()
+    while len(ts) < passes and (len(ts) < min_passes or time.perf_counter() - t_all < budget_s):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), float(np.median(ts)), len(ts)
+
+
+def oracle_build_prefix(orc, wl, budget_s, cores, cap):
+    """CPU construction (the reference's path: one addPoint per row, here on every core) over as long a prefix
+    of the prescribed base stream as the time budget allows.  Returns (oracle, rows kept, seconds)."""
+    d = wl["d"]
+    o = orc.OracleHNSW(d, wl["metric"], cap)
+    kept, built, t0 = [], 0, time.perf_counter()
+    step = 20000
+    for first, x in gen_chunks(cap, d, BASE_SEED):
+        off = 0
+        while off < x.shape[0] and time.perf_counter() - t0 < budget_s:
+            m = min(step, x.shape[0] - off)
+            o.add(x[off:off + m], np.arange(built, built + m, dtype=np.uint64), threads=cores)
+            built += m
+            off += m
+        kept.append(x[:off])
+        if off < x.shape[0] or time.perf_counter() - t0 >= budget_s:
+            break
+    return o, np.concatenate(kept) if kept else np.empty((0, d), np.float32), time.perf_counter() - t0
 
 
 # ---------------------------------------------------------------------------------------------
 def run_reference(args, wl):
-    """The reference arm: the CPU oracle (hnswlib restatement; oracle/_ref cannot exist because the
-    hnswlib headers are not in /root/reference) with every host thread, its own CPU-built graph."""
+    """The reference arm: the CPU oracle (hnswlib restatement; oracle/_ref cannot exist because the hnswlib
+    headers are not in /root/reference) with every host thread pinned, its own CPU-built graph."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as orc
 
-    cores = host_cores()
+    orc.set_thread_pinning(True)
+    cpus = host_cpus()
+    cores = len(cpus)
+    info = host_info()
     N, d, Q, k, ef = wl["N"], wl["d"], wl["Q"], wl["k"], wl["ef"]
-    # bounded sample: CPU construction is the slow part (reference: one addPoint per row)
-    budget_s = 100.0
-    base = gen(N, d, BASE_SEED)
+    brute = bool(wl.get("brute"))
     q = gen(Q, d, QUERY_SEED)
-    o = orc.OracleHNSW(d, wl["metric"], N)
-    built, t0, chunk = 0, time.time(), 20000
-    while built < N and time.time() - t0 < budget_s:
-        m = min(chunk, N - built)
-        o.add(base[built:built + m], np.arange(built, built + m, dtype=np.uint64), threads=cores)
-        built += m
-    t_build = time.time() - t0
-    o.set_ef(ef)
-    for _ in range(args.warmup):
-        o.search(q, k, ef=ef, threads=cores)
-    t0 = time.time()
-    for _ in range(args.steps):
-        labels, _, _ = o.search(q, k, ef=ef, threads=cores)
-    dt = (time.time() - t0) / args.steps
-    gt, _ = orc.bruteforce(base[:built], q[:200], k, wl["metric"], threads=cores)
-    qps = Q / dt
-    sample = (f"graph built on the CPU over the first {built} of {N} base vectors in {t_build:.0f}s "
-              f"({cores} threads); each step = all {Q} queries at ef={ef}")
+    if brute:
+        ns, qs = min(N, 200_000), min(Q, 256)
+        base = gen(ns, d, BASE_SEED)
+        best, med, passes = timed_passes(lambda: orc.bruteforce(base, q[:qs], k, wl["metric"], threads=cores), 3, 2, 60)
+        qps = qs / med * (ns / N)
+        sample = (f"oracle exact scan of {qs} queries over the first {ns} base vectors on {cores} pinned threads, "
+                  f"scaled by {ns}/{N}; median of {passes} passes")
+        built, rec, t_build, steps_ms = ns, 1.0, 0.0, [med * 1e3]
+    else:
+        o, base, t_build = oracle_build_prefix(orc, wl, args.ref_build_budget, cores, min(N, args.ref_max_points))
+        built = base.shape[0]
+        o.set_ef(ef)
+        for _ in range(max(args.warmup, 1)):
+            o.search(q, k, ef=ef, threads=cores)
+        steps_ms = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            labels, _, _ = o.search(q, k, ef=ef, threads=cores)
+            steps_ms.append((time.perf_counter() - t0) * 1e3)
+        med = float(np.median(steps_ms)) * 1e-3
+        best = min(steps_ms) * 1e-3
+        gt, _ = orc.bruteforce(base, q[:200], k, wl["metric"], threads=cores)
+        rec = recall_at_k(labels[:200], gt)
+        qps = Q / med
+        sample = (f"graph built on the CPU over the first {built} of {N} base vectors in {t_build:.0f}s ({cores} pinned "
+                  f"threads); each step = all {Q} queries at ef={ef}; value = Q / median step time of {args.steps} steps")
     line = {
         "impl": "reference", "metric": "k-NN queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "N": N, "N_sample": built, "d": d, "Q": Q, "k": k, "ef": ef,
                    "metric_space": wl["metric"]},
-        "recall_at_k": recall_at_k(labels[:200], gt),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "recall_at_k": rec,
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                         "best_queries_per_s": (Q if not brute else qs * ns / N) / best, "build_s": round(t_build, 1),
+                         "step_ms_min_median_max": [min(steps_ms), float(np.median(steps_ms)), max(steps_ms)],
+                         "pinned": True, **info},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
+def parity_block(ehb, orc, wl, budget_s, cores, device):
+    """Recall parity at a matched sub-sample N' (SURVEY.md §8d parity gate), same data, same queries, same ef."""
+    d, k, ef, metric = wl["d"], wl["k"], wl["ef"], wl["metric"]
+    nq = 1000
+    q = gen(nq, d, QUERY_SEED)
+    o, base, t_cpu = oracle_build_prefix(orc, wl, budget_s, cores, min(wl["N"], 1_000_000))
+    n1 = base.shape[0]
+    ix = ehb.NativeIndex(d, metric=metric, capacity=n1, device=device)
+    ix.add(base)
+    t0 = time.perf_counter()
+    ix.build()
+    t_gpu = time.perf_counter() - t0
+    gt, _, _ = ix.search_bruteforce(q, k)
+    ol, od, _ = o.search(q, k, ef=ef, threads=cores)
+    gl, gd, _ = ix.search(q, k, ef=ef)
+    o2 = orc.OracleHNSW(d, metric, n1)
+    o2.import_graph(ix.export_graph())
+    xl, xd, _ = o2.search(q, k, ef=ef, threads=cores)
+    same = gl == xl
+    rel = float(np.max(np.abs(gd[same] - xd[same]) / np.maximum(np.abs(xd[same]), 1e-6))) if same.any() else None
+    out = {"N_prime": n1, "queries": nq, "ef": ef, "k": k,
+           "recall_oracle_built_oracle_walk": recall_at_k(ol, gt),
+           "recall_gpu_built_gpu_walk": recall_at_k(gl, gt),
+           "recall_gpu_built_oracle_walk": recall_at_k(xl, gt),
+           "ids_equal_gpu_vs_oracle_walk_same_graph": float(same.mean()),
+           "max_rel_dist_err_same_graph": rel,
+           "cpu_build_s": round(t_cpu, 1), "gpu_build_s": round(t_gpu, 2),
+           "gate": "recall(GPU) >= recall(oracle) at the same ef; |dist - oracle dist| <= 1e-4 relative"}
+    out["gate_passed"] = bool(out["recall_gpu_built_gpu_walk"] >= out["recall_oracle_built_oracle_walk"] - 0.005 and
+                              (rel is None or rel <= 1e-4))
+    del ix, o, o2
+    return out
+
+
 def run_ehb(args, wl):
     import torch
     import torch.distributed as dist
@@ -199,13 +333,14 @@ def run_ehb(args, wl):
     N, d, Q, k, ef, metric = wl["N"], wl["d"], wl["Q"], wl["k"], wl["ef"], wl["metric"]
     brute = bool(wl.get("brute"))
     steps, warmup = args.steps, max(args.warmup, 3)
+    t_setup0 = time.time()
 
-    # ---- build the shard (setup, untimed) ---------------------------------------------------
-    t0 = time.time()
-    base = gen(N, d, BASE_SEED + 1000 * rank)
-    labels0 = np.arange(rank * N, (rank + 1) * N, dtype=np.uint64)  # global labels: contiguous ranges
+    # ---- build the shard (setup, untimed): generated chunk by chunk, added as it comes -----------------
     ix = ehb.NativeIndex(d, metric=metric, capacity=N, device=local)
-    ix.add(base, labels0)
+    t0 = time.time()
+    for first, x in prefetched(gen_chunks(N, d, BASE_SEED + 1000 * rank)):
+        ix.add(x, np.arange(rank * N + first, rank * N + first + x.shape[0], dtype=np.uint64))  # global labels
+    t_ingest = time.time() - t0
     t1 = time.time()
     if not brute:
         ix.build()
@@ -219,11 +354,11 @@ def run_ehb(args, wl):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     from embeddinghub_b200.sharded import ShardedSearcher
 
-    searcher = ShardedSearcher(ix, world, local)
+    searcher = ShardedSearcher(ix, world, local, exchange=args.exchange)
     last = {}
 
     def step_dev(i):
-        # per-shard walk -> (world > 1: one all-gather of the per-shard top-k -> merge kernel)
+        # per-shard walk -> (world > 1: ONE exchange step: push + flag + merge kernel over peer memory)
         last["l"], last["d"], last["c"] = searcher.search_dev(dq[i % len(dq)], k, ef, sptr, bruteforce=brute,
                                                               precision=1 if brute else 0)
 
@@ -232,7 +367,7 @@ def run_ehb(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input timing: K steps, L2 flushed between steps, device events --------------
+    # ---- resident-input timing: K steps, L2 flushed between steps, device events --------------------------
     for i in range(warmup):
         step_dev(i)
     barrier()
@@ -240,24 +375,43 @@ def run_ehb(args, wl):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    kernel_ms, alg_bytes = [], []
+    kernel_ms, alg_bytes, counters = [], [], []
     barrier()
     for i in range(steps):
         flush.zero_()            # untimed: evicts L2 between timed iterations
         ev[i][0].record(stream)
         step_dev(warmup + i)
         ev[i][1].record(stream)
-        if i < 4 or i == steps - 1:   # kernel duration + counters of this launch (syncs on its events)
+        if i < 4 or i == steps - 1:   # kernel duration + counters of THIS launch (syncs on its events)
             ev[i][1].synchronize()
             kernel_ms.append(ix.last_kernel_ms())
-            alg_bytes.append(0 if brute else ix.stats()["algorithmic_bytes"])
+            s_i = ix.stats()
+            alg_bytes.append(0 if brute else s_i["algorithmic_bytes"])
+            counters.append(s_i)
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
     clocks = sampler.stop() if rank == 0 else None
-    st = ix.stats()
+    st = counters[-1]
+    kernel_name = ix.last_kernel_name()
     labels_dev = last["l"].cpu().numpy().view(np.uint64).copy()
 
-    # ---- end to end through the host entry point (pinned host buffers) ------------------------
+    # the local shard alone (no exchange), same steps: lets a reader separate the walk from the exchange
+    shard_ms = None
+    if world > 1:
+        solo = ShardedSearcher(ix, 1, local)
+        for i in range(2):
+            solo.search_dev(dq[i % len(dq)], k, ef, sptr, bruteforce=brute, precision=1 if brute else 0)
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(steps, 10))]
+        for i, (a, b) in enumerate(ev2):
+            flush.zero_()
+            a.record(stream)
+            solo.search_dev(dq[(warmup + i) % len(dq)], k, ef, sptr, bruteforce=brute, precision=1 if brute else 0)
+            b.record(stream)
+        barrier()
+        shard_ms = sum(a.elapsed_time(b) for a, b in ev2) / len(ev2)
+
+    # ---- end to end through the host entry point (pinned host buffers) ------------------------------------
     hq = [torch.from_numpy(x).pin_memory() for x in qsets]
     hl = torch.empty((Q, k), dtype=torch.int64).pin_memory()
     hd = torch.empty((Q, k), dtype=torch.float32).pin_memory()
@@ -276,7 +430,7 @@ def run_ehb(args, wl):
             check(L.ehb_index_search(h, Q, C.c_void_p(hq[i % len(hq)].data_ptr()), k, ef,
                                      C.c_void_p(hl.data_ptr()), C.c_void_p(hd.data_ptr()), C.c_void_p(hc.data_ptr())))
         else:
-            # sharded: H2D of the queries, per-shard walk, all-gather, merge, D2H of the merged result
+            # sharded: H2D of the queries, per-shard walk, exchange + merge, D2H of the merged result
             dq_e2e.copy_(hq[i % len(hq)], non_blocking=True)
             ml_, md_, mc_ = searcher.search_dev(dq_e2e, k, ef, sptr, bruteforce=brute, precision=1 if brute else 0)
             hl.copy_(ml_, non_blocking=True)
@@ -291,6 +445,8 @@ def run_ehb(args, wl):
     for i in range(steps):
         flush.zero_()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0e = time.perf_counter()
         step_e2e(warmup + i)     # returns after the D2H of the results completed
         t_e2e += time.perf_counter() - t0e
@@ -298,98 +454,117 @@ def run_ehb(args, wl):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms, shard_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = t[0].item(), t[1].item()
+        dev_ms, e2e_ms, shard_ms = t[0].item(), t[1].item(), t[2].item()
 
-    # ---- recall vs exact ground truth (own kernels: exact fp32 brute force) ---------------------
+    # ---- recall vs exact ground truth (own kernels: exact fp32 brute force, same exchange + merge) -----------
     qi = (warmup + steps - 1) % len(dq)
-    gl_t, _, _ = searcher.search_dev(dq[qi], k, ef, sptr, bruteforce=True)   # exact, same exchange + merge
+    nrec = min(Q, args.recall_queries)
+    gl_t, _, _ = searcher.search_dev(dq[qi][:nrec].contiguous(), k, ef, sptr, bruteforce=True)
     torch.cuda.synchronize()
     gt_l = gl_t.cpu().numpy().view(np.uint64).copy()
-    rec = recall_at_k(labels_dev, gt_l)
+    rec = recall_at_k(labels_dev[:nrec], gt_l)
+    timed_out = 0
+    if world > 1 and searcher.exchange == "peer":
+        tmo = C.c_uint32()
+        check(L.ehb_exchange_timed_out(searcher._ex, C.byref(tmo)))
+        timed_out = tmo.value
 
     if rank != 0:
         if world > 1:
+            dist.barrier()          # rank 0 may still run its CPU legs
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the walk kernel ------------------------------------------------------------
+    # ---- roofline of the walk kernel ------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    if peaks:
+        peak, peak_src = peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     k_ms = float(np.mean(kernel_ms))
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload)
+        tj = json.load(open(tpath))
+        ent = tj.get(args.workload)
+        if isinstance(ent, dict):
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
+        elif ent is not None:
+            traffic = ent
     if brute:
-        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
         tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
         flops = 2.0 * Q * N * d
         ach = flops / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
                     "traffic": traffic, "peak_source": "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
-                    if peaks else "fallback (B200_PROFILING.md)", "kernel": "bf16_dist_gemm_kernel + select/merge + "
-                    "fp32 re-rank (whole brute-force pipeline; the GEMM tiles are written to HBM and re-read by the "
-                    "selection — not fused yet)", "kernel_ms": k_ms, "flops_per_launch": flops}
+                    if peaks else "fallback (B200_PROFILING.md)", "kernel": "bf16_topk_gemm_kernel (persistent tcgen05 "
+                    "GEMM, selection fused into the epilogue) + compaction + fp32 re-rank: the whole brute-force "
+                    "pipeline is timed", "kernel_ms": k_ms, "flops_per_launch": flops}
     else:
         achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": "hnsw_search_kernel", "kernel_ms": k_ms,
-                    "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
-                    "evals_per_query": st["dist_evals"] / Q, "hops_per_query": st["hops_base"] / Q}
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
+                    "kernel_ms": k_ms, "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
+                    "evals_per_query": st["dist_evals"] / Q, "hops_per_query": st["hops_base"] / Q,
+                    "visited_overflow_queries": st["visited_overflow"]}
 
-    # ---- CPU baseline: the oracle walks the SAME graph with the SAME queries (N=1 only) ---------
-    cpu = None
+    # ---- CPU legs (rank 0): baseline on the SAME graph (N=1) and the recall parity block --------------------
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        orc.set_thread_pinning(True)
+        cores = len(host_cpus())
+        info = host_info()
     if world == 1 and not args.no_cpu_baseline and brute:
-        from oracle import oracle as orc
-
-        cores = host_cores()
         ns, qs = min(N, 200_000), min(Q, 256)
-        t0c = time.time()
-        orc.bruteforce(base[:ns], qsets[qi][:qs], k, metric, threads=cores)
-        dtc = time.time() - t0c
-        cpu = {"value": qs / dtc * (ns / N), "unit": "queries/s", "cores": cores, "kind": "port",
+        base_s = gen(ns, d, BASE_SEED)
+        best, med, passes = timed_passes(lambda: orc.bruteforce(base_s, qsets[qi][:qs], k, metric, threads=cores), 3, 2, 60)
+        cpu = {"value": qs / med * (ns / N), "unit": "queries/s", "cores": cores, "kind": "port", "pinned": True, **info,
                "sample": f"oracle exact scan (hnswlib BruteforceSearch semantics) of {qs} queries over the first {ns} base "
-                         f"vectors on {cores} threads, scaled by {ns}/{N} to the full base set"}
+                         f"vectors on {cores} pinned threads, scaled by {ns}/{N} to the full base set; median of {passes}"}
     elif world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-
-        cores = host_cores()
         g = ix.export_graph()
         o = orc.OracleHNSW(d, metric, N)
         o.import_graph(g)
         del g
         qq = qsets[qi]  # the oracle normalises cosine queries itself
-        o.search(qq[:100], k, ef=ef, threads=cores)
-        reps, t0c = 0, time.time()
-        while reps < 3 or (time.time() - t0c < 8 and reps < 50):
-            cl, _, _ = o.search(qq, k, ef=ef, threads=cores)
-            reps += 1
-        cpu_qps = Q * reps / (time.time() - t0c)
-        t0c = time.time()
-        o.search(qq, k, ef=ef, threads=1)
-        cpu_1t = Q / (time.time() - t0c)
+        res = {}
+
+        def one_pass():
+            res["l"] = o.search(qq, k, ef=ef, threads=cores)[0]
+
+        best, med, passes = timed_passes(one_pass, 5, 3, 40)
+        cl = res["l"]
+        t0c = time.perf_counter()
+        o.search(qq[:max(Q // 20, 50)], k, ef=ef, threads=1)
+        cpu_1t = max(Q // 20, 50) / (time.perf_counter() - t0c)
         # "reference as shipped": the reference never calls setEf, so it runs ef = max(10, k) (index.cc:14-15,41)
         ef_ship = max(10, k)
-        t0c, reps_s = time.time(), 0
-        while reps_s < 3 or (time.time() - t0c < 3 and reps_s < 50):
-            sl, _, _ = o.search(qq, k, ef=ef_ship, threads=cores)
-            reps_s += 1
-        ship_cpu = Q * reps_s / (time.time() - t0c)
+
+        def ship_pass():
+            res["s"] = o.search(qq, k, ef=ef_ship, threads=cores)[0]
+
+        sbest, smed, _ = timed_passes(ship_pass, 3, 2, 15)
         for _ in range(3):
             gl_s, _, _ = ix.search(qsets[qi], k, ef=ef_ship)
         ship_ms = ix.last_kernel_ms()
-        shipped = {"ef": ef_ship, "gpu_kernel_queries_per_s": Q / (ship_ms * 1e-3), "gpu_recall_at_k": recall_at_k(gl_s, gt_l),
-                   "cpu_queries_per_s": ship_cpu, "cpu_recall_at_k": recall_at_k(sl, gt_l), "cpu_threads": cores}
-        cpu = {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port", "reference_as_shipped": shipped,
+        shipped = {"ef": ef_ship, "gpu_kernel_queries_per_s": Q / (ship_ms * 1e-3),
+                   "gpu_recall_at_k": recall_at_k(gl_s[:nrec], gt_l), "cpu_queries_per_s": Q / smed,
+                   "cpu_recall_at_k": recall_at_k(res["s"][:nrec], gt_l), "cpu_threads": cores}
+        cpu = {"value": Q / med, "unit": "queries/s", "cores": cores, "kind": "port", "pinned": True, **info,
+               "best_queries_per_s": Q / best, "median_queries_per_s": Q / med, "passes": passes,
+               "reference_as_shipped": shipped,
                "sample": f"oracle (hnswlib restatement) searching the same {N}-point graph exported from the GPU "
-                         f"build, same {Q} queries, ef={ef}; {reps} passes on {cores} threads",
-               "single_thread_queries_per_s": cpu_1t, "recall_at_k": recall_at_k(cl, gt_l),
+                         f"build, same {Q} queries, ef={ef}; median of {passes} passes on {cores} pinned threads",
+               "single_thread_queries_per_s": cpu_1t, "recall_at_k": recall_at_k(cl[:nrec], gt_l),
                "ids_equal_to_gpu_frac": float(np.mean(cl == labels_dev))}
+        del o
+    if not args.no_cpu_baseline and not args.no_parity and not brute:
+        parity = parity_block(ehb, orc, wl, args.parity_budget, cores, local)
 
     h2d = Q * d * 4
     d2h = Q * k * 12 + Q * 4
@@ -397,26 +572,33 @@ def run_ehb(args, wl):
     if brute:  # pad + 2x to_bf16 (first step) + per (q-chunk, n-chunk): GEMM, select, merge + fill + re-rank
         nchunks = -(-Q // 2048) * -(-N // 131072)
         launches_per_step = 3 + 3 * nchunks + 2 + (1 if world > 1 else 0)
+    global_qps = Q / (dev_ms * 1e-3)
     line = {
-        "metric": "k-NN queries/s", "value": world * Q / (dev_ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "metric": "k-NN queries/s", "value": global_qps, "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic" if DIST == "gaussian" else "synthetic (gmm)",
         "config": {"workload": wl["desc"], "N_per_gpu": N, "N_total": N * world, "d": d, "Q": Q, "k": k, "ef": ef,
                    "metric_space": metric, "M": 16, "ef_construction": 200, "path": "bruteforce bf16 tcgen05 + fp32 re-rank" if brute else "graph walk", "l2": "flushed between timed steps "
                    "(256 MB write) and the index (vectors+links) is larger than L2", "parallelism":
-                   f"range-sharded x{world}, one all-gather of per-shard top-k + merge" if world > 1 else "single GPU",
-                   "build_s": round(t_build, 2), "setup_s": round(time.time() - t0, 1)},
-        "global_queries_per_s": Q / (dev_ms * 1e-3),
-        "recall_at_k": rec,
-        "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                   f"range-sharded x{world}, one {searcher.exchange} exchange of per-shard top-k + merge" if world > 1 else "single GPU",
+                   "exchange": searcher.exchange, "build_s": round(t_build, 2), "ingest_s": round(t_ingest, 1),
+                   "setup_s": round(time.time() - t_setup0, 1)},
+        "shard_searches_per_s": world * global_qps,
+        "shard_only_ms_per_step": shard_ms,
+        "recall_at_k": rec, "recall_queries": nrec,
+        "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
         "gpu_launches": launches_per_step * steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "clocks": clocks,
     }
+    if timed_out:
+        line["exchange_timed_out"] = True
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -426,12 +608,21 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ehb200", choices=["ehb200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-budget", type=float, default=45.0, help="seconds of CPU construction for the parity block")
+    ap.add_argument("--ref-build-budget", type=float, default=100.0)
+    ap.add_argument("--ref-max-points", type=int, default=1_000_000)
+    ap.add_argument("--recall-queries", type=int, default=2000)
     ap.add_argument("--dist", default="gaussian", choices=["gaussian", "gmm"])
     args = ap.parse_args()
     global DIST
     DIST = args.dist
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if args.workload == "auto":
+        args.workload = "c3" if max(world, args.gpus) == 1 else "c5"
     wl = dict(WORKLOADS[args.workload])
     if DIST != "gaussian":
         wl["desc"] += " [secondary distribution: 1024-centre GMM, sigma 0.3]"

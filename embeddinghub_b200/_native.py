@@ -83,6 +83,7 @@ SYMBOLS = {
     "ehb_index_search_bruteforce_dev": (C.c_int, [_VP, _U64, _VP, _U32, C.c_int, _VP, _VP, _VP, _VP]),
     "ehb_index_stats": (C.c_int, [_VP, C.POINTER(Stats)]),
     "ehb_index_last_kernel_ms": (C.c_int, [_VP, C.POINTER(C.c_float)]),
+    "ehb_index_last_kernel_name": (C.c_int, [_VP, C.c_char_p, _U32]),
     "ehb_index_export_graph": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(_U32), C.POINTER(_I32)]),
     "ehb_index_import_graph": (C.c_int, [_VP, _U64, _VP, _VP, _VP, _VP, _VP, _U64, _VP, _U32, _I32]),
     "ehb_index_save": (C.c_int, [_VP, C.c_char_p]),
@@ -271,6 +272,11 @@ class NativeIndex:
         ms = C.c_float()
         check(lib().ehb_index_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_kernel_name(self):
+        buf = C.create_string_buffer(96)
+        check(lib().ehb_index_last_kernel_name(self._h, buf, 96))
+        return buf.value.decode()
 
     # -- graph exchange -------------------------------------------------------------
     def export_graph(self):

@@ -503,6 +503,16 @@ int ehb_index::search_dev(ehb::SearchSlot* sl, uint64_t nq, const float* dq, uin
   CU(cudaEventRecord(sl->ev1, s));
   sl->last_nq = nq;
   {
+    const uint32_t kpl = ef_eff <= 64 ? 2 : (ef_eff <= 128 ? 4 : (ef_eff <= 256 ? 8 : 16));
+    const uint32_t lpv = dpad > 256 ? 32 : 8;
+    if (team >= 2)
+      std::snprintf(sl->last_kernel, sizeof(sl->last_kernel), "hnsw_search_team_kernel<NQ=%u,KPL=%u,T=%u>",
+                    dpad / (4 * lpv), kpl, team);
+    else
+      std::snprintf(sl->last_kernel, sizeof(sl->last_kernel), "hnsw_search_kernel<LPV=%u,NQ=%u,KPL=%u>", lpv,
+                    dpad / (4 * lpv), kpl);
+  }
+  {
     std::lock_guard<std::mutex> g(last_mu);
     last_slot = sl;
     last_was_brute = false;
@@ -924,6 +934,15 @@ int ehb_index_last_kernel_ms(ehb_index* ix, float* out_ms) {
   cudaEvent_t e1 = ix->last_was_brute ? ix->bf_ev1 : ix->last_slot->ev1;
   CU(cudaEventSynchronize(e1));
   CU(cudaEventElapsedTime(out_ms, e0, e1));
+  return EHB_OK;
+}
+
+int ehb_index_last_kernel_name(ehb_index* ix, char* out, uint32_t out_bytes) {
+  ENTER_S(ix);
+  if (!out || !out_bytes) return fail(EHB_ERR_INVALID, "null out");
+  std::lock_guard<std::mutex> g(ix->last_mu);
+  const char* name = !ix->timed ? "" : (ix->last_was_brute ? "bruteforce" : ix->last_slot->last_kernel);
+  std::snprintf(out, out_bytes, "%s", name);
   return EHB_OK;
 }
 

@@ -118,6 +118,7 @@ struct SearchSlot {
   DevBuf<unsigned long long> stat_sum;
   PinBuf h_q, h_l, h_d, h_c;
   uint64_t last_nq = 0;
+  char last_kernel[64] = {0};  // name of the graph-walk kernel of the most recent search on this slot
   ~SearchSlot() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);

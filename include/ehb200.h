@@ -154,6 +154,8 @@ int ehb_index_stats(ehb_index* ix, ehb_stats* out);
  * CUDA events recorded around the kernel(s): milliseconds of the graph-walk (or
  * brute-force) kernels alone.  Synchronises on those events. */
 int ehb_index_last_kernel_ms(ehb_index* ix, float* out_ms);
+/* Name (with template arguments) of the graph-walk kernel that search launched. */
+int ehb_index_last_kernel_name(ehb_index* ix, char* out, uint32_t out_bytes);
 
 /* Graph exchange (hnswlib saveIndex/loadIndex are never called by the
  * reference; persistence is a "next" row).  Layout:

@@ -33,6 +33,9 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -550,6 +553,10 @@ struct Oracle {
 
 thread_local std::string g_err;
 
+// Timing hygiene for the CPU baseline (bench.py): with pinning on, worker t runs on the t-th CPU of the
+// process affinity mask, so a pass is not at the mercy of the scheduler migrating 128 threads.
+std::atomic<int> g_pin_threads{0};
+
 template <class F>
 void parallel_for(size_t n, int threads, F f) {
   if (threads <= 1 || n < 2) {
@@ -560,8 +567,21 @@ void parallel_for(size_t n, int threads, F f) {
   std::vector<std::thread> ts;
   std::mutex em;
   std::string err;
+  std::vector<int> cpus;
+  if (g_pin_threads.load()) {
+    cpu_set_t mask;
+    if (sched_getaffinity(0, sizeof(mask), &mask) == 0)
+      for (int c = 0; c < CPU_SETSIZE; ++c)
+        if (CPU_ISSET(c, &mask)) cpus.push_back(c);
+  }
   for (int t = 0; t < threads; ++t)
-    ts.emplace_back([&] {
+    ts.emplace_back([&, t] {
+      if (!cpus.empty()) {
+        cpu_set_t one;
+        CPU_ZERO(&one);
+        CPU_SET(cpus[(size_t)t % cpus.size()], &one);
+        pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+      }
       try {
         for (;;) {
           size_t i = next.fetch_add(1);
@@ -583,6 +603,7 @@ void parallel_for(size_t n, int threads, F f) {
 extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
+void orc_set_thread_pinning(int on) { g_pin_threads = on; }
 
 void* orc_create(uint64_t dim, int metric, uint64_t max_elements, uint64_t M, uint64_t efc, uint64_t seed) {
   try {

@@ -174,6 +174,11 @@ class OracleHNSW:
             _ptr(np.ascontiguousarray(g["up_off"], np.uint32)), _ptr(lu), int(g["entry"]), int(g["maxlevel"])))
 
 
+def set_thread_pinning(on=True):
+    """Worker t of every parallel pass pins itself to the t-th CPU of the process affinity mask."""
+    lib().orc_set_thread_pinning(1 if on else 0)
+
+
 def bruteforce(base, q, k, metric="l2", threads=1):
     """Exact k-NN, canonical sequential-FMA fp32 arithmetic, order (dist, row)."""
     base, q = _f32(base), _f32(q)
