@@ -8,13 +8,11 @@ this image, protoc-generated stubs are not usable with its protobuf runtime).
 
 Request handling delegates to embeddinghub_b200.hub.EmbeddingHub, which mirrors the semantics and
 status codes of EmbeddingHubService (embeddingstore/server.cc:65-233).  The reference serialises
-every RPC under one mutex (server.cc:175) and answers one query per call; here concurrent
-NearestNeighbor calls are coalesced by a micro-batcher into one batched GPU search (the batched
-call the reference's docs promise, docs/inference.md:14-22).
+every RPC under one mutex (server.cc:175) and answers one query per call; here RPC threads call the
+library concurrently and its combining queue (csrc/api.cu) coalesces their single-query searches into
+batched launches.  The batched call the reference's docs promise (docs/inference.md:14-22) is served
+by a side service, EmbeddingHubBatch.MultiNearestNeighbor, so the reference proto stays untouched.
 """
-import queue
-import threading
-import time
 from concurrent import futures
 
 import grpc
@@ -101,52 +99,13 @@ _CODES = {"NOT_FOUND": grpc.StatusCode.NOT_FOUND, "INVALID_ARGUMENT": grpc.Statu
           "FAILED_PRECONDITION": grpc.StatusCode.FAILED_PRECONDITION, "ALREADY_EXISTS": grpc.StatusCode.ALREADY_EXISTS}
 
 
-class _NNBatcher:
-    """Coalesces concurrent embedding-mode NearestNeighbor calls on one space into one batched search."""
-
-    def __init__(self, hub, space, max_batch=256, max_wait_s=0.0005):
-        self.hub, self.space, self.max_batch, self.max_wait_s = hub, space, max_batch, max_wait_s
-        self.q = queue.Queue()
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
-
-    def submit(self, num, embedding):
-        slot = {"num": num, "emb": embedding, "ev": threading.Event(), "res": None, "err": None}
-        self.q.put(slot)
-        slot["ev"].wait()
-        if slot["err"] is not None:
-            raise slot["err"]
-        return slot["res"]
-
-    def _run(self):
-        while True:
-            first = self.q.get()
-            batch = [first]
-            deadline = time.perf_counter() + self.max_wait_s
-            while len(batch) < self.max_batch:
-                left = deadline - time.perf_counter()
-                try:
-                    batch.append(self.q.get(timeout=max(left, 0)) if left > 0 else self.q.get_nowait())
-                except queue.Empty:
-                    break
-            try:
-                kmax = max(s["num"] for s in batch)
-                res = self.hub.multi_nearest_neighbor(self.space, kmax, embeddings=[s["emb"] for s in batch])
-                for s, r in zip(batch, res):
-                    s["res"] = r[: s["num"]]
-            except Exception as e:  # noqa: BLE001 - forwarded to every waiter
-                for s in batch:
-                    s["err"] = e
-            for s in batch:
-                s["ev"].set()
-
-
 class EmbeddingHubServicer:
-    def __init__(self, hub=None, device=0, batch=True):
+    """Thread-per-RPC like the reference's sync server, but WITHOUT its global mutex (server.cc:175): every
+    NearestNeighbor call goes straight into ehb_index_search, whose combining queue turns the concurrent
+    single-query calls of many RPC threads into batched launches.  One malformed request fails alone."""
+
+    def __init__(self, hub=None, device=0):
         self.hub = hub or EmbeddingHub(device=device)
-        self.batch = batch
-        self._batchers = {}
-        self._lock = threading.Lock()
 
     def _fail(self, context, e):
         context.abort(_CODES.get(e.code, grpc.StatusCode.UNKNOWN), e.message)
@@ -205,19 +164,37 @@ class EmbeddingHubServicer:
     def NearestNeighbor(self, req, context):
         has_vec = len(req.embedding.values) != 0
         try:
-            if self.batch and has_vec and not req.key:
-                self.hub._space(req.space)  # NOT_FOUND before queueing
-                with self._lock:
-                    b = self._batchers.get(req.space)
-                    if b is None:
-                        b = self._batchers[req.space] = _NNBatcher(self.hub, req.space)
-                keys = b.submit(req.num, list(req.embedding.values))
-            else:
-                keys = self.hub.nearest_neighbor(req.space, req.num, key=req.key,
-                                                 embedding=list(req.embedding.values) if has_vec else None)
+            keys = self.hub.nearest_neighbor(req.space, req.num, key=req.key,
+                                             embedding=list(req.embedding.values) if has_vec else None)
         except HubError as e:
             self._fail(context, e)
         return M["NearestNeighborResponse"](keys=keys)
+
+    def MultiNearestNeighbor(self, req_iter, context):
+        """Side service (EmbeddingHubBatch): docs/inference.md:14-22 promises multi_nearest_neighbor but
+        embedding_store.proto has no RPC for it and must stay byte-for-byte, so the batched form lives beside it:
+        a stream of NearestNeighborRequest in, the matching NearestNeighborResponse stream out (same order), all
+        embedding-mode requests of one (space, num) answered by ONE batched search."""
+        reqs = list(req_iter)
+        out = [None] * len(reqs)
+        groups = {}
+        for i, r in enumerate(reqs):
+            if len(r.embedding.values) != 0 and not r.key:
+                groups.setdefault((r.space, r.num), []).append(i)
+        try:
+            for (space, num), idx in groups.items():
+                res = self.hub.multi_nearest_neighbor(space, num, embeddings=[list(reqs[i].embedding.values) for i in idx])
+                for i, keys in zip(idx, res):
+                    out[i] = keys
+            for i, r in enumerate(reqs):
+                if out[i] is None:
+                    has_vec = len(r.embedding.values) != 0
+                    out[i] = self.hub.nearest_neighbor(r.space, r.num, key=r.key,
+                                                       embedding=list(r.embedding.values) if has_vec else None)
+        except HubError as e:
+            self._fail(context, e)
+        for keys in out:
+            yield M["NearestNeighborResponse"](keys=keys)
 
     def Download(self, req, context):
         try:
@@ -244,10 +221,21 @@ def _handlers(servicer):
     return grpc.method_handlers_generic_handler(SERVICE, h)
 
 
+BATCH_SERVICE = PKG + ".EmbeddingHubBatch"
+
+
+def _batch_handlers(servicer):
+    h = {"MultiNearestNeighbor": grpc.stream_stream_rpc_method_handler(
+        servicer.MultiNearestNeighbor, M["NearestNeighborRequest"].FromString,
+        M["NearestNeighborResponse"].SerializeToString)}
+    return grpc.method_handlers_generic_handler(BATCH_SERVICE, h)
+
+
 def make_server(address=DEFAULT_ADDRESS, device=0, max_workers=32, hub=None):
     """Returns (grpc server, bound port).  RunServer of embeddingstore/server.cc:249-268."""
     server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
-    server.add_generic_rpc_handlers((_handlers(EmbeddingHubServicer(hub=hub, device=device)),))
+    servicer = EmbeddingHubServicer(hub=hub, device=device)
+    server.add_generic_rpc_handlers((_handlers(servicer), _batch_handlers(servicer)))
     port = server.add_insecure_port(address)
     return server, port
 
@@ -262,6 +250,9 @@ class Stub:
             kind = (channel.stream_stream if cs and ss else channel.stream_unary if cs else
                     channel.unary_stream if ss else channel.unary_unary)
             setattr(self, name, kind(path, request_serializer=se, response_deserializer=de))
+        self.MultiNearestNeighbor = channel.stream_stream(
+            f"/{BATCH_SERVICE}/MultiNearestNeighbor", request_serializer=M["NearestNeighborRequest"].SerializeToString,
+            response_deserializer=M["NearestNeighborResponse"].FromString)
 
 
 def main(argv=None):

@@ -33,7 +33,7 @@ class EmbeddingHub:
     def __init__(self, device=0):
         self._spaces = {}
         self._device = device
-        self._mu = threading.Lock()  # mutations exclusive; searches are serialised inside the library
+        self._mu = threading.Lock()  # guards the space table and host key maps; searches run concurrently
 
     # server.cc:65-75
     def create_space(self, name, dims, metric="l2"):
@@ -65,7 +65,31 @@ class EmbeddingHub:
         if sp.immutable:
             raise HubError("FAILED_PRECONDITION", "Cannot write to immutable space")  # server.cc:124-127
         with self._mu:
-            sp.index.multiset(items)
+            try:
+                sp.index.multiset(items)
+            except ValueError as e:          # wrong embedding length: the caller's fault, nothing was stored
+                raise HubError("INVALID_ARGUMENT", str(e)) from None
+
+    # docs/reading_and_writing_embeddings.md:49-66
+    def delete(self, space, key):
+        self.multidelete(space, [key])
+
+    def multidelete(self, space, keys):
+        sp = self._space(space)
+        if sp.immutable:
+            raise HubError("FAILED_PRECONDITION", "Cannot write to immutable space")
+        with self._mu:
+            try:
+                sp.index.multidelete(keys)
+            except KeyError:
+                raise HubError("NOT_FOUND", "Key not found") from None
+
+    def delete_all(self, space):
+        sp = self._space(space)
+        if sp.immutable:
+            raise HubError("FAILED_PRECONDITION", "Cannot write to immutable space")
+        with self._mu:
+            sp.index.delete_all()
 
     # server.cc:98-111 / 151-170
     def get(self, space, key):
@@ -85,6 +109,8 @@ class EmbeddingHub:
     def multi_nearest_neighbor(self, space, num, keys=None, embeddings=None, ef=0):
         """Batched NearestNeighbor (docs/inference.md:14-22: promised, never implemented upstream)."""
         sp = self._space(space)
+        if num < 0 or num > 2047:
+            raise HubError("INVALID_ARGUMENT", "num must be in 0..2047")
         has_key = bool(keys)
         has_vec = embeddings is not None and len(embeddings) != 0
         if has_key and has_vec:
@@ -105,4 +131,10 @@ class EmbeddingHub:
                     r = r[:-1] if len(r) > num else r
                 out.append(r[:num])
             return out
-        return sp.index.approx_nearest_batch(np.asarray(embeddings, np.float32), num, ef)
+        try:
+            q = np.asarray(embeddings, np.float32)
+        except ValueError:
+            raise HubError("INVALID_ARGUMENT", "embeddings have different lengths") from None
+        if q.ndim != 2 or q.shape[1] != sp.dims:
+            raise HubError("INVALID_ARGUMENT", f"embedding length must be {sp.dims}")
+        return sp.index.approx_nearest_batch(q, num, ef)

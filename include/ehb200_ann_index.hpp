@@ -77,6 +77,15 @@ class ANNIndex {
 
   void set_ef(uint32_t ef) { check(ehb_index_set_ef(ix_, ef)); }
 
+  // docs/reading_and_writing_embeddings.md:49-66 (space.delete): tombstone, never returned again; a later
+  // set() of the same key brings it back (hnswlib markDelete / addPoint).
+  void remove(const std::string& key) {
+    auto it = key_to_label_.find(key);
+    if (it == key_to_label_.end()) throw std::runtime_error("ANNIndex::remove: unknown key");
+    uint64_t label = it->second;
+    check(ehb_index_remove(ix_, 1, &label));
+  }
+
  private:
   static void check(int rc) {
     if (rc != EHB_OK) throw std::runtime_error(std::string("ehb200: ") + ehb_last_error());

@@ -6,7 +6,8 @@
 // Pinecone (provider/pinecone.go:348-373).
 //
 // NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no Go toolchain here
-// (`go version` -> not found).  The file is written against the interfaces
+// (`go version` -> not found).  The call pattern it produces — many OS threads, one query per call — is
+// exercised against the same C ABI by tests/cpp/concurrent_search.c (64 pthreads).  The file is written against the interfaces
 // cited inline and is meant to be dropped into the reference at
 // provider/b200_vector.go (see INTEGRATION.md for the registration hunks).
 package provider
@@ -22,6 +23,7 @@ import "C"
 import (
 	"encoding/json"
 	"fmt"
+	"runtime"
 	"sync"
 	"unsafe"
 
@@ -38,7 +40,17 @@ type B200VectorConfig struct {
 	EfConstruction uint32 `json:"EfConstruction"`
 	EfSearch       uint32 `json:"EfSearch"`
 	Device         int32  `json:"Device"`
+	Devices        []int32 `json:"Devices"` // more than one entry: range-sharded over those GPUs (ehb_sharded_*)
 	Seed           uint64 `json:"Seed"`
+}
+
+// Serialize — the counterpart every provider config has (provider_config/pinecone_config.go:29-35).
+func (c *B200VectorConfig) Serialize() pc.SerializedConfig {
+	config, err := json.Marshal(c)
+	if err != nil {
+		panic(err)
+	}
+	return config
 }
 
 func (c *B200VectorConfig) Deserialize(config pc.SerializedConfig) error {
@@ -78,8 +90,21 @@ func (s *b200VectorStore) Close() error {
 
 func tableKey(feature, variant string) string { return feature + "\x00" + variant }
 
+// ehb_last_error() is thread-local in the library and goroutines migrate between OS threads, so every call
+// whose failure message is read runs between runtime.LockOSThread / UnlockOSThread (see callLocked).
 func lastError(rc C.int, what string) error {
 	return fferr.NewInternalError(fmt.Errorf("ehb200 %s: status %d: %s", what, int(rc), C.GoString(C.ehb_last_error())))
+}
+
+// callLocked runs fn (one cgo call returning a status) and, on failure, reads the thread-local error text
+// on the same OS thread.
+func callLocked(what string, fn func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := fn(); rc != C.EHB_OK {
+		return lastError(rc, what)
+	}
+	return nil
 }
 
 // CreateIndex — provider/online.go:56.  dims come from types.VectorType (provider/types/value_type.go:96-100).
@@ -103,10 +128,11 @@ func (s *b200VectorStore) CreateIndex(feature, variant string, vectorType types.
 	p.M, p.ef_construction, p.ef_search = C.uint32_t(s.cfg.M), C.uint32_t(s.cfg.EfConstruction), C.uint32_t(s.cfg.EfSearch)
 	p.seed, p.device = C.uint64_t(s.cfg.Seed), C.int32_t(s.cfg.Device)
 	var ix *C.ehb_index
-	if rc := C.ehb_index_create(&p, &ix); rc != C.EHB_OK {
-		return nil, lastError(rc, "create")
+	if err := callLocked("create", func() C.int { return C.ehb_index_create(&p, &ix) }); err != nil {
+		return nil, err
 	}
-	t := &b200Table{ix: ix, dim: int(vectorType.Dimension), labels: map[string]uint64{}}
+	t := &b200Table{ix: ix, dim: int(vectorType.Dimension), labels: map[string]uint64{},
+		cosine: p.metric == C.EHB_COSINE, originals: map[string][]float32{}}
 	s.tables[key] = t
 	return t, nil
 }
@@ -152,6 +178,11 @@ type b200Table struct {
 	mu     sync.RWMutex
 	labels map[string]uint64
 	keys   []string
+	// The index stores cosine rows normalised (hnswlib's convention).  Get must return what Set stored
+	// (vectorstore_test.go testGetSet: reflect.DeepEqual; Redis and Pinecone return the original), so for
+	// cosine tables the original rows are kept host-side, like offlinehub keeps its own copy.
+	cosine    bool
+	originals map[string][]float32
 }
 
 // Set — provider/online.go:51; value must be []float32 (cf. pinecone.go:199-207, redis.go:407-413).
@@ -167,26 +198,48 @@ func (t *b200Table) Set(entity string, value interface{}) error {
 		t.labels[entity] = label
 		t.keys = append(t.keys, entity)
 	}
+	if t.cosine {
+		t.originals[entity] = append([]float32(nil), vec...)
+	}
 	t.mu.Unlock()
 	// Go memory is only borrowed for the duration of the call (cgo pointer rules): the library copies.
-	rc := C.ehb_index_add(t.ix, 1, (*C.float)(unsafe.Pointer(&vec[0])), (*C.uint64_t)(unsafe.Pointer(&label)))
-	if rc != C.EHB_OK {
-		return lastError(rc, "add")
+	return callLocked("add", func() C.int {
+		return C.ehb_index_add(t.ix, 1, (*C.float)(unsafe.Pointer(&vec[0])), (*C.uint64_t)(unsafe.Pointer(&label)))
+	})
+}
+
+// Delete — tombstones the entity (docs: space.delete / multidelete; ehb_index_remove).
+func (t *b200Table) Delete(entity string) error {
+	t.mu.Lock()
+	label, ok := t.labels[entity]
+	delete(t.originals, entity)
+	t.mu.Unlock()
+	if !ok {
+		return fferr.NewEntityNotFoundError("", "", entity, nil)
 	}
-	return nil
+	return callLocked("remove", func() C.int { return C.ehb_index_remove(t.ix, 1, (*C.uint64_t)(unsafe.Pointer(&label))) })
 }
 
 // Get — provider/online.go:52
 func (t *b200Table) Get(entity string) (interface{}, error) {
 	t.mu.RLock()
 	label, ok := t.labels[entity]
+	var orig []float32
+	if ok && t.cosine {
+		orig = t.originals[entity]
+	}
 	t.mu.RUnlock()
 	if !ok {
 		return nil, fferr.NewEntityNotFoundError("", "", entity, nil)
 	}
+	if orig != nil {
+		return append([]float32(nil), orig...), nil
+	}
 	out := make([]float32, t.dim)
-	if rc := C.ehb_index_get(t.ix, C.uint64_t(label), (*C.float)(unsafe.Pointer(&out[0]))); rc != C.EHB_OK {
-		return nil, lastError(rc, "get")
+	if err := callLocked("get", func() C.int {
+		return C.ehb_index_get(t.ix, C.uint64_t(label), (*C.float)(unsafe.Pointer(&out[0])))
+	}); err != nil {
+		return nil, err
 	}
 	return out, nil
 }
@@ -201,11 +254,19 @@ func (t *b200Table) Nearest(feature, variant string, vector []float32, k int32) 
 	}
 	labels := make([]uint64, k)
 	var count C.uint32_t
+	// One goroutine per request, one vector per call (serving.go:744-771): the library's combining queue
+	// coalesces the concurrent calls into batched launches, so no batching is needed on the Go side.
+	runtime.LockOSThread()
 	rc := C.ehb_index_search(t.ix, 1, (*C.float)(unsafe.Pointer(&vector[0])), C.uint32_t(k), 0,
 		(*C.uint64_t)(unsafe.Pointer(&labels[0])), nil, &count)
+	var msg string
+	if rc != C.EHB_OK {
+		msg = C.GoString(C.ehb_last_error())
+	}
+	runtime.UnlockOSThread()
 	if rc != C.EHB_OK {
 		return nil, fferr.NewResourceExecutionError(pt.B200VectorOnline.String(), feature, variant, fferr.ENTITY,
-			fmt.Errorf("%s", C.GoString(C.ehb_last_error())))
+			fmt.Errorf("%s", msg))
 	}
 	t.mu.RLock()
 	defer t.mu.RUnlock()

@@ -15,7 +15,7 @@ class FakeNative:
     """Exact L2 k-NN with insert-or-update by label: the contract of NativeIndex the mirrors rely on."""
 
     def __init__(self, dim, metric="l2", capacity=128, device=0, **kw):
-        self.dim, self.vec, self.order = int(dim), {}, []
+        self.dim, self.vec, self.order, self.dead = int(dim), {}, [], set()
 
     def add(self, vecs, labels=None):
         vecs = np.asarray(vecs, np.float32).reshape(-1, self.dim)
@@ -25,16 +25,28 @@ class FakeNative:
             if l not in self.vec:
                 self.order.append(l)
             self.vec[l] = v.copy()
+            self.dead.discard(l)
 
     def get(self, label):
+        if int(label) in self.dead:
+            raise KeyError(label)
         return self.vec[int(label)].copy()
+
+    def remove(self, labels):
+        for l in np.atleast_1d(labels):
+            if int(l) not in self.vec:
+                raise KeyError(l)
+            self.dead.add(int(l))
+
+    def search_bruteforce(self, q, k, precision=0):
+        return self.search(q, k)
 
     def set_ef(self, ef):
         pass
 
     def search(self, q, k, ef=0):
         q = np.asarray(q, np.float32).reshape(-1, self.dim)
-        labs = np.array(self.order, np.uint64)
+        labs = np.array([l for l in self.order if l not in self.dead], np.uint64)
         out_l = np.full((len(q), k), np.uint64(0xFFFFFFFFFFFFFFFF))
         out_d = np.full((len(q), k), np.inf, np.float32)
         cnt = np.zeros(len(q), np.uint32)
@@ -116,6 +128,43 @@ def test_hub_semantics_and_status_codes():
         hub.get("s", "a")
 
 
+def test_bad_rows_leave_the_index_untouched_and_deletes_follow_the_docs():
+    """a wrong-length embedding must not register its key; docs/reading_and_writing_embeddings.md:49-66."""
+    hub = hub_mod.EmbeddingHub()
+    hub.create_space("s", 2)
+    hub.multiset("s", EMB)
+    with pytest.raises(hub_mod.HubError) as e:
+        hub.multiset("s", [("e", [1, 2]), ("bad", [1, 2, 3])])
+    assert e.value.code == "INVALID_ARGUMENT"
+    with pytest.raises(hub_mod.HubError) as e:
+        hub.set("s", "one", [7])                                   # no silent broadcast of a length-1 row
+    assert e.value.code == "INVALID_ARGUMENT"
+    sp = hub._space("s")
+    assert "e" not in sp.index and "bad" not in sp.index and "one" not in sp.index and len(sp.index) == 4
+    for bad in ([1, 2, 3], [1]):
+        with pytest.raises(hub_mod.HubError) as e:
+            hub.nearest_neighbor("s", 1, embedding=bad)
+        assert e.value.code == "INVALID_ARGUMENT"
+    with pytest.raises(hub_mod.HubError) as e:
+        hub.nearest_neighbor("s", -1, embedding=[1, 0])
+    assert e.value.code == "INVALID_ARGUMENT"
+    assert len(hub.nearest_neighbor("s", 600, embedding=[1, 0])) == 4   # beyond the beam limit: exact scan answers
+    hub.delete("s", "a")
+    assert hub.nearest_neighbor("s", 1, embedding=[0.9, 0.1]) == ["d"]
+    with pytest.raises(hub_mod.HubError) as e:
+        hub.get("s", "a")
+    assert e.value.code == "NOT_FOUND"
+    with pytest.raises(hub_mod.HubError) as e:
+        hub.delete("s", "a")
+    assert e.value.code == "NOT_FOUND"
+    assert sorted(sp.index.keys()) == ["b", "c", "d"] and len(sp.index) == 3
+    hub.set("s", "a", [1, 0])                                      # re-set un-deletes
+    assert hub.nearest_neighbor("s", 1, embedding=[0.9, 0.1]) == ["a"]
+    hub.multidelete("s", ["b", "c"])
+    hub.delete_all("s")
+    assert sp.index.keys() == [] and hub.nearest_neighbor("s", 2, embedding=[1, 0]) == []
+
+
 def test_grpc_roundtrip_over_the_wire():
     import concurrent.futures as cf
 
@@ -131,7 +180,7 @@ def test_grpc_roundtrip_over_the_wire():
         stub.CreateSpace(M["CreateSpaceRequest"](name="s", dims=2))
         stub.MultiSet(iter([M["MultiSetRequest"](key=k, embedding=emb(v), space="s") for k, v in EMB]))
         assert list(stub.NearestNeighbor(M["NearestNeighborRequest"](num=2, space="s", key="a")).keys) == ["d", "b"]
-        with cf.ThreadPoolExecutor(8) as ex:   # concurrent calls go through the micro-batcher
+        with cf.ThreadPoolExecutor(8) as ex:   # concurrent RPC threads call the library directly
             outs = list(ex.map(lambda i: list(stub.NearestNeighbor(M["NearestNeighborRequest"](
                 num=1, space="s", embedding=emb([1, 0] if i % 2 else [0, 1]))).keys), range(32)))
         assert outs == [["a"] if i % 2 else ["b"] for i in range(32)]
@@ -139,5 +188,20 @@ def test_grpc_roundtrip_over_the_wire():
             stub.Get(M["GetRequest"](key="a", space="missing"))
         assert e.value.code() == grpc.StatusCode.NOT_FOUND
         assert sorted(r.key for r in stub.Download(M["DownloadRequest"](space="s"))) == ["a", "b", "c", "d"]
+        # one malformed request fails alone (INVALID_ARGUMENT), its concurrent neighbours succeed
+        def call(i):
+            try:
+                return list(stub.NearestNeighbor(M["NearestNeighborRequest"](
+                    num=1, space="s", embedding=emb([1, 0, 5] if i == 7 else [1, 0]))).keys)
+            except grpc.RpcError as err:
+                return err.code()
+        with cf.ThreadPoolExecutor(8) as ex:
+            outs = list(ex.map(call, range(16)))
+        assert outs[7] == grpc.StatusCode.INVALID_ARGUMENT and all(o == ["a"] for i, o in enumerate(outs) if i != 7)
+        # the side service: batched nearest neighbour on the wire (docs/inference.md:14-22)
+        reqs = [M["NearestNeighborRequest"](num=1, space="s", embedding=emb([1, 0])),
+                M["NearestNeighborRequest"](num=2, space="s", key="a"),
+                M["NearestNeighborRequest"](num=1, space="s", embedding=emb([0, 1]))]
+        assert [list(r.keys) for r in stub.MultiNearestNeighbor(iter(reqs))] == [["a"], ["d", "b"], ["b"]]
     finally:
         server.stop(0)
