@@ -8,7 +8,7 @@ SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := embeddinghub_b200/libehb200.so
 
-all: $(LIB) oracle tests/cpp/ann_index_cases tests/cpp/concurrent_search
+all: $(LIB) oracle tests/cpp/ann_index_cases tests/cpp/concurrent_search tests/cpp/sharded_two_dev
 
 # the reference's ANNIndex unit-test cases against the C++ drop-in twin (run by tests/test_gpu_host.py)
 tests/cpp/ann_index_cases: tests/cpp/ann_index_cases.cc include/ehb200_ann_index.hpp $(LIB)
@@ -17,6 +17,10 @@ tests/cpp/ann_index_cases: tests/cpp/ann_index_cases.cc include/ehb200_ann_index
 # 64 pthreads issuing Q=1 searches through the C ABI (the cgo goroutine pattern; run by tests/test_gpu_round2.py)
 tests/cpp/concurrent_search: tests/cpp/concurrent_search.c include/ehb200.h $(LIB)
 	gcc -std=c11 -O2 -D_POSIX_C_SOURCE=200809L -Iinclude $< -Lembeddinghub_b200 -lehb200 -lpthread -lm -Wl,-rpath,'$$ORIGIN/../../embeddinghub_b200' -o $@
+
+# n_dev = 2 through the C ABI (run by tests/test_gpu_round2.py)
+tests/cpp/sharded_two_dev: tests/cpp/sharded_two_dev.c include/ehb200.h $(LIB)
+	gcc -std=c11 -O2 -Iinclude $< -Lembeddinghub_b200 -lehb200 -lm -Wl,-rpath,'$$ORIGIN/../../embeddinghub_b200' -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/ehb200.h
 	@mkdir -p $(OBJDIR)

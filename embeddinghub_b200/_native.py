@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libehb200.so")
+LIB_PATH = os.environ.get("EHB200_LIB") or os.path.join(_HERE, "libehb200.so")  # EHB200_LIB: A/B builds (tools/)
 
 NO_LABEL = np.uint64(0xFFFFFFFFFFFFFFFF)
 METRICS = {"l2": 0, "ip": 1, "cosine": 2}
@@ -68,6 +68,7 @@ SYMBOLS = {
     "ehb_last_error": (C.c_char_p, []),
     "ehb_abi_version": (_U32, []),
     "ehb_params_default": (None, [C.POINTER(Params), _U32]),
+    "ehb_device_count": (C.c_int, [C.POINTER(_I32)]),
     "ehb_index_create": (C.c_int, [C.POINTER(Params), C.POINTER(_VP)]),
     "ehb_index_destroy": (C.c_int, [_VP]),
     "ehb_index_add": (C.c_int, [_VP, _U64, _VP, _VP]),

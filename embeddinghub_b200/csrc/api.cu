@@ -77,6 +77,7 @@ ehb::WalkCfg ehb_index::walk_cfg(uint32_t ef_eff, uint32_t smem_list, uint64_t j
     uint32_t per_cta = (227u * 1024u) / want;
     uint32_t avail = per_cta > fixed + 1024u ? (per_cta - fixed) / 4u : 256u;
     hs = std::min(roomy, std::max(tight, avail));
+    if (n_deleted) hs = roomy;  // tombstoned candidates rely on the visited table alone (no result-set filter)
   }
   c.hash_size = ehb::align_up(std::max(hs, 256u), 32);
   // stay inside the 227 KB per-block limit
@@ -422,12 +423,12 @@ int ehb_index::build() {
 }
 
 // Searches link pending points lazily; that needs the writer side of the lock.
-int ehb_index::ensure_built(std::shared_lock<std::shared_mutex>& lk) {
+int ehb_index::ensure_built(std::shared_lock<ehb::RwLock>& lk) {
   while (needs_build()) {
     lk.unlock();
     int rc;
     {
-      std::unique_lock<std::shared_mutex> x(rw);
+      std::unique_lock<ehb::RwLock> x(rw);
       rc = build();
     }
     lk.lock();
@@ -595,11 +596,11 @@ int ehb_index::bruteforce_dev(uint64_t nq, const float* dq, uint32_t k, int prec
 // ============================================================================================
 #define ENTER_X(ix)                                                    \
   if (!(ix)) return fail(EHB_ERR_INVALID, "null index handle");        \
-  std::unique_lock<std::shared_mutex> _g((ix)->rw);                    \
+  std::unique_lock<ehb::RwLock> _g((ix)->rw);                    \
   CU(cudaSetDevice((ix)->device))
 #define ENTER_S(ix)                                                    \
   if (!(ix)) return fail(EHB_ERR_INVALID, "null index handle");        \
-  std::shared_lock<std::shared_mutex> _g((ix)->rw);                    \
+  std::shared_lock<ehb::RwLock> _g((ix)->rw);                    \
   CU(cudaSetDevice((ix)->device))
 
 namespace {
@@ -722,6 +723,18 @@ extern "C" {
 
 const char* ehb_last_error(void) { return ehb::g_err.c_str(); }
 uint32_t ehb_abi_version(void) { return 2; }
+
+int ehb_device_count(int32_t* out) {
+  if (!out) return fail(EHB_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out = 0;
+    return fail(EHB_ERR_CUDA, std::string("no CUDA device (ehb200 has no CPU fallback): ") + cudaGetErrorString(e));
+  }
+  *out = n;
+  return EHB_OK;
+}
 
 void ehb_params_default(ehb_params* p, uint32_t dim) {
   std::memset(p, 0, sizeof(*p));

@@ -107,6 +107,46 @@ struct PinBuf {
   }
 };
 
+// Reader/writer lock that prefers writers: once a mutation waits, new searches queue behind it, so a stream
+// of overlapping searches can never starve an add (glibc's rwlock, which std::shared_mutex wraps, prefers
+// readers by default).  Meets the SharedMutex requirements used by std::shared_lock / std::unique_lock.
+class RwLock {
+ public:
+  void lock() {
+    std::unique_lock<std::mutex> g(mu_);
+    ++writers_waiting_;
+    cv_.wait(g, [&] { return !writer_ && readers_ == 0; });
+    --writers_waiting_;
+    writer_ = true;
+  }
+  void unlock() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      writer_ = false;
+    }
+    cv_.notify_all();
+  }
+  void lock_shared() {
+    std::unique_lock<std::mutex> g(mu_);
+    cv_.wait(g, [&] { return !writer_ && writers_waiting_ == 0; });
+    ++readers_;
+  }
+  void unlock_shared() {
+    bool wake;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      wake = --readers_ == 0;
+    }
+    if (wake) cv_.notify_all();
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  uint32_t readers_ = 0, writers_waiting_ = 0;
+  bool writer_ = false;
+};
+
 // Everything one in-flight graph search needs.
 struct SearchSlot {
   cudaStream_t stream = nullptr;
@@ -156,7 +196,7 @@ struct ehb_index {
   int sms = 148;
   cudaStream_t stream = nullptr;  // mutation / construction / brute-force stream
   cudaEvent_t bf_ev0 = nullptr, bf_ev1 = nullptr;
-  std::shared_mutex rw;
+  ehb::RwLock rw;
 
   uint64_t cap = 0;        // vector capacity
   uint64_t n = 0;          // stored vectors (tombstones included, like hnswlib cur_element_count)
@@ -239,7 +279,7 @@ struct ehb_index {
   ehb::BuildGraph build_graph() const;
   int build();
   bool needs_build() const { return n_linked != n || !pending_updates.empty(); }
-  int ensure_built(std::shared_lock<std::shared_mutex>& lk);
+  int ensure_built(std::shared_lock<ehb::RwLock>& lk);
   int acquire_slot(ehb::SearchSlot** out);
   void release_slot(ehb::SearchSlot* sl, cudaStream_t used);
   int search_dev(ehb::SearchSlot* sl, uint64_t nq, const float* dq, uint32_t k, uint32_t ef_in, uint64_t* dl, float* dd,

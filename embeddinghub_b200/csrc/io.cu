@@ -185,7 +185,7 @@ extern "C" {
 int ehb_index_export_graph(ehb_index* ix, float* vectors, uint64_t* labels, uint8_t* levels, uint32_t* links0,
                            uint32_t* up_off, uint32_t* links_up, uint32_t* entry, int32_t* max_level) {
   if (!ix) return fail(EHB_ERR_INVALID, "null index handle");
-  std::unique_lock<std::shared_mutex> g(ix->rw);
+  std::unique_lock<ehb::RwLock> g(ix->rw);
   CU(cudaSetDevice(ix->device));
   RET(ix->build());
   cudaStream_t s = ix->stream;
@@ -208,7 +208,7 @@ int ehb_index_import_graph(ehb_index* ix, uint64_t n, const float* vectors, cons
                            const uint8_t* levels, const uint32_t* links0, const uint32_t* up_off, uint64_t upper_rows,
                            const uint32_t* links_up, uint32_t entry, int32_t max_level) {
   if (!ix) return fail(EHB_ERR_INVALID, "null index handle");
-  std::unique_lock<std::shared_mutex> g(ix->rw);
+  std::unique_lock<ehb::RwLock> g(ix->rw);
   CU(cudaSetDevice(ix->device));
   if (n && (!vectors || !labels || !levels || !links0 || !up_off)) return fail(EHB_ERR_INVALID, "null buffer");
   if (upper_rows && !links_up) return fail(EHB_ERR_INVALID, "null links_up");
@@ -253,7 +253,7 @@ static uint64_t file_bytes(const ehb_params& p, uint64_t n, uint64_t rows) {
 
 int ehb_index_save(ehb_index* ix, const char* path) {
   if (!ix || !path) return fail(EHB_ERR_INVALID, "null argument");
-  std::unique_lock<std::shared_mutex> g(ix->rw);  // one consistent snapshot: no add can slip in between
+  std::unique_lock<ehb::RwLock> g(ix->rw);  // one consistent snapshot: no add can slip in between
   CU(cudaSetDevice(ix->device));
   RET(ix->build());
   FILE* f = std::fopen(path, "wb");
@@ -306,7 +306,7 @@ int ehb_index_load(const char* path, int32_t device, ehb_index** out) {
     p.device = device;
     p.capacity = std::max<uint64_t>(n, 1);
     RET(ehb_index_create(&p, &ix));
-    std::unique_lock<std::shared_mutex> g(ix->rw);
+    std::unique_lock<ehb::RwLock> g(ix->rw);
     cudaStream_t s = ix->stream;
     RET(ix->ensure_upper(std::max<uint64_t>(rows, 1)));
     Pipe pipe(s);

@@ -5,7 +5,7 @@
 namespace ehb {
 
 template <int LPV, int NQ, int KPL>
-__global__ void __launch_bounds__(128) hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
+__global__ void __launch_bounds__(128, 4) hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
                                                           uint32_t nq, uint32_t k, uint32_t ef,
                                                           uint64_t* __restrict__ out_labels,
                                                           float* __restrict__ out_dists,

@@ -325,6 +325,7 @@ __device__ __forceinline__ uint32_t ul_worst(const UList<KPL>& u) {
   for (int s = 1; s < KPL; ++s) m = max(m, u.hi[s]);
   return __reduce_max_sync(0xffffffffu, m);
 }
+#ifdef EHB_ULIST_V1  // A/B only: the round-1 form (one ballot + branch per slot)
 // Insert (hi, id) [warp-uniform]; cnt/worst_hi are maintained by the caller's copies.
 // Precondition when cnt == ef: hi < worst_hi.
 template <int KPL>
@@ -382,6 +383,64 @@ __device__ __forceinline__ uint32_t ul_min_unexpanded(UList<KPL>& u, bool mark, 
   }
   return node;
 }
+#else
+// Insert (hi, id) [warp-uniform]; cnt/worst_hi are maintained by the caller's copies.
+// Precondition when cnt == ef: hi < worst_hi (the true maximum over the occupied positions).
+// Each lane first reduces over its OWN KPL slots (which slot is free / holds my largest key), then ONE
+// ballot elects the lane: the cost is independent of KPL apart from register-local selects (v1 walked the
+// slots with one ballot + branch each: ~KPL dependent warp collectives per insert).
+template <int KPL>
+__device__ __forceinline__ void ul_insert(UList<KPL>& u, uint32_t hi, uint32_t id, uint32_t ef, uint32_t& cnt,
+                                          uint32_t& worst_hi, uint32_t lane) {
+  if (cnt < ef) {
+    int es = -1;  // my first free (valid, empty) slot
+#pragma unroll
+    for (int s = KPL - 1; s >= 0; --s)
+      if (u.id[s] == kInvalid && u.hi[s] == 0xFFFFFFFFu) es = s;
+    const uint32_t b = __ballot_sync(0xffffffffu, es >= 0);
+    if (b && (int)lane == __ffs(b) - 1) {
+#pragma unroll
+      for (int s = 0; s < KPL; ++s)
+        if (s == es) u.hi[s] = hi, u.id[s] = id;
+    }
+    cnt++;
+    if (cnt == ef) worst_hi = ul_worst<KPL>(u);
+  } else {
+    uint32_t m = 0;
+    int ms = -1;  // my slot holding the largest key among occupied slots
+#pragma unroll
+    for (int s = 0; s < KPL; ++s)
+      if (u.id[s] != kInvalid && (ms < 0 || u.hi[s] > m)) m = u.hi[s], ms = s;
+    const uint32_t b = __ballot_sync(0xffffffffu, ms >= 0 && m == worst_hi);
+    if (b && (int)lane == __ffs(b) - 1) {
+#pragma unroll
+      for (int s = 0; s < KPL; ++s)
+        if (s == ms) u.hi[s] = hi, u.id[s] = id;
+    }
+    worst_hi = ul_worst<KPL>(u);
+  }
+}
+// closest unexpanded entry: returns its id (flag clear) or kInvalid; mark=true sets its expanded flag
+template <int KPL>
+__device__ __forceinline__ uint32_t ul_min_unexpanded(UList<KPL>& u, bool mark, uint32_t lane) {
+  uint32_t m = 0xFFFFFFFFu, mid = kInvalid;
+  int ms = -1;  // my closest unexpanded slot (empty / dead slots carry the flag bit in kInvalid)
+#pragma unroll
+  for (int s = 0; s < KPL; ++s)
+    if (!(u.id[s] & kExpandedFlag) && (ms < 0 || u.hi[s] < m)) m = u.hi[s], mid = u.id[s], ms = s;
+  const uint32_t best = __reduce_min_sync(0xffffffffu, m);
+  const uint32_t b = __ballot_sync(0xffffffffu, ms >= 0 && m == best);
+  if (!b) return kInvalid;
+  const int l = __ffs(b) - 1;
+  const uint32_t node = __shfl_sync(0xffffffffu, mid, l);
+  if (mark && (int)lane == l) {
+#pragma unroll
+    for (int s = 0; s < KPL; ++s)
+      if (s == ms) u.id[s] |= kExpandedFlag;
+  }
+  return node;
+}
+#endif
 // ordered distance of the closest unexpanded entry (0xFFFFFFFF when there is none)
 template <int KPL>
 __device__ __forceinline__ uint32_t ul_min_unexpanded_hi(const UList<KPL>& u) {
@@ -584,20 +643,28 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
   uint32_t node = ep;
   if (ep_result) node = ul_min_unexpanded<KPL>(u, true, c.lane);
   uint32_t nb = load_row(g, node, level, c.lane);
+  const uint32_t hop_limit = 64u * ef + 4096u;  // a walk expands each admitted node once; this only guards
+  uint32_t hops = 0;                             // against a corrupt graph
   for (;;) {
     if (level == 0) wc.hops_base++; else wc.hops_upper++;
+    if (++hops > hop_limit) break;
     __syncwarp();
     // speculative: the row of the closest entry still unexpanded
     const uint32_t spec = ul_min_unexpanded<KPL>(u, false, c.lane);
     uint32_t spec_row = kInvalid;
     if (spec != kInvalid) spec_row = load_row(g, spec & kIdMask, level, c.lane);
     bool is_new = false;
-    if (nb != kInvalid) is_new = hash_insert(c, nb, ovf);
+    uint32_t o = 0;  // this insert ran out of probes: "new" is then only a guess
+    if (nb != kInvalid && nb != exclude) is_new = hash_insert(c, nb, o);
+    ovf |= o;
     __syncwarp();  // hash probing diverges; reconverge before the collective section
     uint32_t mask = __ballot_sync(0xffffffffu, is_new);
     uint32_t m = __popc(mask);
     if (m) {
-      if (is_new) c.cand_id[__popc(mask & lanemask_lt())] = nb;
+      const uint32_t pos = __popc(mask & lanemask_lt());
+      if (is_new) c.cand_id[pos] = nb;
+      // tombstones only: candidates (compacted positions) whose visited status is a guess
+      const uint32_t unsure = del ? __reduce_or_sync(0xffffffffu, (is_new && o) ? (1u << pos) : 0u) : 0u;
       __syncwarp();
       wc.evals += m;
       eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
@@ -622,7 +689,9 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
         uint32_t ij = __shfl_sync(0xffffffffu, myid, j);
         if (cnt >= ef && hj >= worst_hi) continue;
         if ((delmask >> j) & 1u) {  // admitted like any candidate, but queued instead of becoming a result
-          dq_push(c, dn, hj, ij, ovf);
+          // (a tombstone whose visited status is only a guess is dropped: nothing else would keep it from
+          //  being queued and expanded again and again once the visited table is full)
+          if (!((unsure >> j) & 1u)) dq_push(c, dn, hj, ij, ovf);
           continue;
         }
         if (ovf_any && ul_contains<KPL>(u, ij)) continue;

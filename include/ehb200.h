@@ -99,6 +99,8 @@ const char* ehb_last_error(void);
 uint32_t ehb_abi_version(void);
 
 void ehb_params_default(ehb_params* p, uint32_t dim);
+/* Number of usable CUDA devices (what a caller sizes device_ids[] from); EHB_ERR_CUDA when there is none. */
+int ehb_device_count(int32_t* out);
 
 /* ANNIndex::ANNIndex(dims, init_cap) — index.cc:10-18 (allocates the hnswlib
  * arena); here: device arrays for vectors, labels, levels and adjacency. */

@@ -23,6 +23,12 @@ def _has_gpu():
 
 def pytest_collection_modifyitems(config, items):
     if _has_gpu():
+        # a wedged kernel or lock must fail the run, not hang it: the timer thread ends the process even when the
+        # main thread sits inside a CUDA call (pytest-timeout, thread method)
+        if config.pluginmanager.hasplugin("timeout"):
+            for it in items:
+                if "gpu" in it.keywords and not it.get_closest_marker("timeout"):
+                    it.add_marker(pytest.mark.timeout(420, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

@@ -82,6 +82,8 @@ def test_concurrent_searches_are_safe():
     ix = ehb.NativeIndex(32, capacity=5000)
     ix.add(base)
     ix.build()
+    ix.set_search_width(2)   # a fixed number of warps per query: concurrent calls are combined into batches of
+                             # varying size, and the automatic width depends on the batch size
     q = rng.standard_normal((64, 32), dtype=np.float32)
     ref = ix.search(q, 5, ef=40)[0]
     errs = []

@@ -337,6 +337,16 @@ def test_sharded_index_matches_single_index(shards):
     assert int(ex1[0][0, 0]) not in ls2[0].tolist()
 
 
+def test_sharded_two_devices_c_program():
+    """tests/cpp/sharded_two_dev.c: n_dev = 2 through include/ehb200.h from plain C (both shards on GPU 0 when the
+    box has one GPU; two GPUs exercise the peer stores into device 0's gather buffer)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "sharded_two_dev")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/sharded_two_dev not built (make)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_exchange_two_ranks_in_one_process():
     """ehb_exchange with both 'ranks' in this process (attach_local instead of CUDA IPC): each rank's search
     writes into its block, one exchange_merge_kernel per rank pushes / flags / waits / merges; both ranks must
