@@ -188,7 +188,36 @@ def host_info():
         load = os.getloadavg()[0]
     except Exception:
         pass
-    return {"cpu_model": model, "nproc": len(host_cpus()), "loadavg_1m_before": load}
+    return {"cpu_model": model, "nproc": len(host_cpus()), "loadavg_1m_before": load,
+            "cgroup_cpu_limit": cgroup_cpu_limit()}
+
+
+def cgroup_cpu_limit():
+    """CPUs' worth of quota the container may use (None = unlimited / unknown)."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
+def calibrate_threads(run, cores, sample_desc):
+    """The CPU arm gets the thread count that serves it best on THIS box: a short sample is timed at
+    nproc, nproc/2, ... (oversubscribed hyper-threads, NUMA and container CPU quotas make "all logical CPUs"
+    the slowest choice on some hosts — round 1 saw 4.4x between two boxes).  run(threads) -> seconds."""
+    cand = sorted({c for c in (cores, cores // 2, cores // 4, cores // 8, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    sweep = {}
+    for c in cand:
+        run(c)                      # warm
+        sweep[c] = min(run(c), run(c))
+    best = min(sweep, key=sweep.get)
+    return best, {"sample": sample_desc, "seconds_by_threads": {str(k): round(v, 4) for k, v in sweep.items()}}
 
 
 def timed_passes(fn, passes=5, min_passes=3, budget_s=30.0):
@@ -202,20 +231,34 @@ def timed_passes(fn, passes=5, min_passes=3, budget_s=30.0):
     return min(ts), float(np.median(ts)), len(ts)
 
 
-def oracle_build_prefix(orc, wl, budget_s, cores, cap):
-    """CPU construction (the reference's path: one addPoint per row, here on every core) over as long a prefix
-    of the prescribed base stream as the time budget allows.  Returns (oracle, rows kept, seconds)."""
+def oracle_build_prefix(orc, wl, budget_s, cores, cap, tune=None):
+    """CPU construction (the reference's path: one addPoint per row, here multi-threaded) over as long a prefix
+    of the prescribed base stream as the time budget allows.  Returns (oracle, rows kept, seconds).  With
+    `tune` (a dict), the thread count is calibrated on the first 20k points and recorded there."""
     d = wl["d"]
     o = orc.OracleHNSW(d, wl["metric"], cap)
     kept, built, t0 = [], 0, time.perf_counter()
     step = 20000
+    threads = cores
     for first, x in gen_chunks(cap, d, BASE_SEED):
         off = 0
         while off < x.shape[0] and time.perf_counter() - t0 < budget_s:
             m = min(step, x.shape[0] - off)
-            o.add(x[off:off + m], np.arange(built, built + m, dtype=np.uint64), threads=cores)
+            o.add(x[off:off + m], np.arange(built, built + m, dtype=np.uint64), threads=threads)
             built += m
             off += m
+            if tune is not None and "threads" not in tune:
+                qs = gen(256, d, QUERY_SEED)
+                t_cal = time.perf_counter()
+
+                def run(c):
+                    t1 = time.perf_counter()
+                    o.search(qs, wl["k"], ef=wl["ef"], threads=c)
+                    return time.perf_counter() - t1
+
+                threads, tune["sweep"] = calibrate_threads(run, cores, f"256 queries on the first {built} points")
+                tune["threads"] = threads
+                t0 += time.perf_counter() - t_cal      # calibration is not construction time
         kept.append(x[:off])
         if off < x.shape[0] or time.perf_counter() - t0 >= budget_s:
             break
@@ -247,8 +290,11 @@ def run_reference(args, wl):
                   f"scaled by {ns}/{N}; median of {passes} passes")
         built, rec, t_build, steps_ms = ns, 1.0, 0.0, [med * 1e3]
     else:
-        o, base, t_build = oracle_build_prefix(orc, wl, args.ref_build_budget, cores, min(N, args.ref_max_points))
+        tune = {}
+        o, base, t_build = oracle_build_prefix(orc, wl, args.ref_build_budget, cores, min(N, args.ref_max_points), tune)
         built = base.shape[0]
+        cores = tune.get("threads", cores)
+        info["thread_sweep"] = tune.get("sweep")
         o.set_ef(ef)
         for _ in range(max(args.warmup, 1)):
             o.search(q, k, ef=ef, threads=cores)
@@ -286,7 +332,9 @@ def parity_block(ehb, orc, wl, budget_s, cores, device):
     d, k, ef, metric = wl["d"], wl["k"], wl["ef"], wl["metric"]
     nq = 1000
     q = gen(nq, d, QUERY_SEED)
-    o, base, t_cpu = oracle_build_prefix(orc, wl, budget_s, cores, min(wl["N"], 1_000_000))
+    tune = {}
+    o, base, t_cpu = oracle_build_prefix(orc, wl, budget_s, cores, min(wl["N"], 1_000_000), tune)
+    cores = tune.get("threads", cores)
     n1 = base.shape[0]
     ix = ehb.NativeIndex(d, metric=metric, capacity=n1, device=device)
     ix.add(base)
@@ -533,6 +581,13 @@ def run_ehb(args, wl):
         del g
         qq = qsets[qi]  # the oracle normalises cosine queries itself
         res = {}
+
+        def cal(c):
+            t1 = time.perf_counter()
+            o.search(qq[:512], k, ef=ef, threads=c)
+            return time.perf_counter() - t1
+
+        cores, info["thread_sweep"] = calibrate_threads(cal, cores, f"512 of the {Q} queries on the full graph")
 
         def one_pass():
             res["l"] = o.search(qq, k, ef=ef, threads=cores)[0]

@@ -14,6 +14,10 @@ const std::string& last_error_text() { return g_err; }
 }  // namespace ehb
 using ehb::fail;
 
+#ifndef EHB_WANT_CAP
+#define EHB_WANT_CAP 16  // resident warps per SM the visited-table sizing aims at (register budget: search_impl.cuh)
+#endif
+
 // ============================================================================================
 // index state
 // ============================================================================================
@@ -70,7 +74,7 @@ ehb::WalkCfg ehb_index::walk_cfg(uint32_t ef_eff, uint32_t smem_list, uint64_t j
     hs = 1u << t_hash_bits;
   } else {
     uint64_t ctas = (jobs + team - 1) / std::max(team, 1u);
-    uint32_t want = (uint32_t)std::min<uint64_t>((ctas + sms - 1) / sms, c.staged ? 5u : 16u / team);
+    uint32_t want = (uint32_t)std::min<uint64_t>((ctas + sms - 1) / sms, c.staged ? 5u : (uint32_t)EHB_WANT_CAP / team);
     want = std::max(want, 4u);
     c.hash_size = 0;
     uint32_t fixed = ehb::warp_smem_bytes(c, dpad) * team + 1024u + (smem_list ? 256u : 0u);

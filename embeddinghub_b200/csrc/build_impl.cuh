@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t heuristic_select(WarpCtx& c, const GraphView
   return nsel;
 }
 
-template <int LPV, int NQ, int KPL>
+template <int LPV, int NQ, int KPL, bool HASDEL>
 __global__ void __launch_bounds__(128) build_search_kernel(BuildGraph bg, WalkCfg cfg, const uint32_t* __restrict__ ids,
                                                            uint32_t first, uint32_t b, int is_update, BuildBuffers bb,
                                                            uint32_t warp_smem) {
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) build_search_kernel(BuildGraph bg, WalkCf
   uint32_t* links0 = const_cast<uint32_t*>(g.links0);
   uint32_t* links_up = const_cast<uint32_t*>(g.links_up);
   for (int level = min(level_p, top); level >= 0; --level) {
-    beam_search<LPV, NQ, KPL, false>(c, g, qr, ul, cur, curdist, level, bg.efc, is_update ? p : kInvalid, wc);
+    beam_search<LPV, NQ, KPL, false, HASDEL>(c, g, qr, ul, cur, curdist, level, bg.efc, is_update ? p : kInvalid, wc);
     // ascending dump into the shared-memory list the selection heuristic walks
     c.cnt = 0;
     for (;;) {
@@ -401,7 +401,7 @@ cudaError_t launch_build_t(const BuildGraph& bg, const WalkCfg& cfg, const uint3
   while (msmem > 200 * 1024 && mwpb > 1) mwpb >>= 1, msmem = (size_t)mwsm * mwpb;
   dim3 grid((b + wpb - 1) / wpb), block(32 * wpb);
   uint32_t ethreads = bb.edge_cap;
-  auto ks = build_search_kernel<LPV, NQ, KPL>;
+  auto ks = bg.g.deleted ? build_search_kernel<LPV, NQ, KPL, true> : build_search_kernel<LPV, NQ, KPL, false>;
   auto km = merge_rows_kernel<LPV, NQ>;
   if (is_update) {
     // updatePoint's neighbour re-selection runs before the moved points are re-linked

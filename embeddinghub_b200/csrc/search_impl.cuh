@@ -4,8 +4,17 @@
 
 namespace ehb {
 
-template <int LPV, int NQ, int KPL>
-__global__ void __launch_bounds__(128, 4) hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
+// Register budget: by default ptxas chooses (128 for the round-1 loop at d=128 / ef=256; an explicit
+// minBlocksPerSM — even 1 — changes its heuristics: 143 registers, and a cap of 4 blocks serialises the
+// 16-vector load batches: 9.1 -> 22.7 ms on the C5 shape).  EHB_SEARCH_MINB (A/B builds only) sets one.
+#ifdef EHB_SEARCH_MINB
+#define EHB_SEARCH_BOUNDS __launch_bounds__(128, EHB_SEARCH_MINB)
+#else
+#define EHB_SEARCH_BOUNDS __launch_bounds__(128)
+#endif
+
+template <int LPV, int NQ, int KPL, bool HASDEL>
+__global__ void EHB_SEARCH_BOUNDS hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
                                                           uint32_t nq, uint32_t k, uint32_t ef,
                                                           uint64_t* __restrict__ out_labels,
                                                           float* __restrict__ out_dists,
@@ -31,7 +40,7 @@ __global__ void __launch_bounds__(128, 4) hnsw_search_kernel(GraphView g, WalkCf
     __syncwarp();
     wc.evals = 1;
     greedy_descent<LPV, NQ>(c, g, qr, cur, curdist, g.max_level, 0, wc);
-    beam_search<LPV, NQ, KPL, true>(c, g, qr, ul, cur, curdist, 0, ef, kInvalid, wc);
+    beam_search<LPV, NQ, KPL, true, HASDEL>(c, g, qr, ul, cur, curdist, 0, ef, kInvalid, wc);
   }
   // nearest-first output: extract the k closest in ascending order
   uint32_t found = 0;
@@ -54,14 +63,14 @@ __global__ void __launch_bounds__(128, 4) hnsw_search_kernel(GraphView g, WalkCf
   }
 }
 
-template <int LPV, int NQ, int KPL>
+template <int LPV, int NQ, int KPL, bool HASDEL>
 cudaError_t launch_search_t(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
                             uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
                             uint32_t* stats, uint32_t wpb, cudaStream_t s) {
   uint32_t wsm = warp_smem_bytes(cfg, g.dpad);
   size_t smem = (size_t)wsm * wpb;
   dim3 grid((nq + wpb - 1) / wpb), block(32 * wpb);
-  auto kern = hnsw_search_kernel<LPV, NQ, KPL>;
+  auto kern = hnsw_search_kernel<LPV, NQ, KPL, HASDEL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, block, smem, s>>>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wsm);
@@ -74,8 +83,11 @@ cudaError_t launch_search_kpl(const GraphView& g, const WalkCfg& cfg, const floa
                               uint32_t* stats, uint32_t wpb, cudaStream_t s) {
   // (Keeping a whole 2M-neighbour hop in flight per batch (~168 registers) was measured on C2:
   //  0.446 ms vs 0.423 ms — no gain, so batches stay at 16 vectors.)
-#define EHB_KPL(K) \
-  return launch_search_t<LPV, NQ, K>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wpb, s)
+#define EHB_KPL(K)                                                                                                   \
+  return g.deleted ? launch_search_t<LPV, NQ, K, true>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, \
+                                                       stats, wpb, s)                                                 \
+                   : launch_search_t<LPV, NQ, K, false>(g, cfg, queries, nq, k, ef, out_labels, out_dists,            \
+                                                        out_counts, stats, wpb, s)
   if (ef <= 64) EHB_KPL(2);
   if (ef <= 128) EHB_KPL(4);
   if (ef <= 256) EHB_KPL(8);

@@ -198,7 +198,10 @@ __device__ __forceinline__ float group_reduce(float acc) {
 }
 
 // ---- LPV = 8: direct 128-bit loads, U steps (4 vectors each) in flight ------
-template <int NQ, int U = (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2))>  // default: 64 registers of loads in flight
+#ifndef EHB_EVAL_UDIV
+#define EHB_EVAL_UDIV 1  // A/B: divide the number of 4-vector load steps kept in flight
+#endif
+template <int NQ, int U = ((NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2)) / EHB_EVAL_UDIV > 0 ? (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2)) / EHB_EVAL_UDIV : 1)>  // default: 64 registers of loads in flight
 __device__ __forceinline__ void eval_direct(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
                                             uint32_t m, int metric) {
   const uint32_t sub = c.lane & 7u, grp = c.lane >> 3;
@@ -620,13 +623,15 @@ __device__ __forceinline__ uint32_t dq_min(const WarpCtx& c, uint32_t dn, uint32
   return b ? __shfl_sync(0xffffffffu, mp, __ffs(b) - 1) : kInvalid;
 }
 
-template <int LPV, int NQ, int KPL, bool PREFETCH>
+// HASDEL = false compiles every trace of the tombstone machinery out (an index without tombstones runs
+// exactly the round-1 loop: the extra live registers cost the 16-vector load batches their overlap).
+template <int LPV, int NQ, int KPL, bool PREFETCH, bool HASDEL>
 __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], UList<KPL>& u,
                                             uint32_t ep, float epdist, int level, uint32_t ef, uint32_t exclude,
                                             WalkCounters& wc) {
   hash_clear(c);
   ul_clear<KPL>(u, ef, c.lane);
-  const uint8_t* __restrict__ del = c.dcap ? g.deleted : nullptr;  // warp-uniform
+  const uint8_t* __restrict__ del = (HASDEL && c.dcap) ? g.deleted : nullptr;  // warp-uniform
   uint32_t dn = 0;                                                  // entries in the deleted-candidate queue
   uint32_t ovf = 0;
   if (c.lane == 0) {
@@ -643,11 +648,10 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
   uint32_t node = ep;
   if (ep_result) node = ul_min_unexpanded<KPL>(u, true, c.lane);
   uint32_t nb = load_row(g, node, level, c.lane);
-  const uint32_t hop_limit = 64u * ef + 4096u;  // a walk expands each admitted node once; this only guards
-  uint32_t hops = 0;                             // against a corrupt graph
   for (;;) {
     if (level == 0) wc.hops_base++; else wc.hops_upper++;
-    if (++hops > hop_limit) break;
+    // a walk expands each admitted node once; the bound only guards against a corrupt graph
+    if (HASDEL && wc.hops_base + wc.hops_upper > 64u * ef + 65536u) break;
     __syncwarp();
     // speculative: the row of the closest entry still unexpanded
     const uint32_t spec = ul_min_unexpanded<KPL>(u, false, c.lane);
@@ -664,7 +668,7 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       const uint32_t pos = __popc(mask & lanemask_lt());
       if (is_new) c.cand_id[pos] = nb;
       // tombstones only: candidates (compacted positions) whose visited status is a guess
-      const uint32_t unsure = del ? __reduce_or_sync(0xffffffffu, (is_new && o) ? (1u << pos) : 0u) : 0u;
+      const uint32_t unsure = (HASDEL && del) ? __reduce_or_sync(0xffffffffu, (is_new && o) ? (1u << pos) : 0u) : 0u;
       __syncwarp();
       wc.evals += m;
       eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
@@ -677,18 +681,18 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       }
       uint32_t myhi = 0xFFFFFFFFu, myid = kInvalid;
       if (c.lane < m) myhi = f2ord(c.cand_dist[c.lane]), myid = c.cand_id[c.lane];
-      const bool mydel = del && c.lane < m && del[myid];
+      const bool mydel = HASDEL && del && c.lane < m && del[myid];
       __syncwarp();
       ovf_any = ovf_any || __any_sync(0xffffffffu, ovf);
       uint32_t qual = __ballot_sync(0xffffffffu, c.lane < m && (cnt < ef || myhi < worst_hi));
-      const uint32_t delmask = del ? __ballot_sync(0xffffffffu, mydel) : 0u;
+      const uint32_t delmask = (HASDEL && del) ? __ballot_sync(0xffffffffu, mydel) : 0u;
       while (qual) {
         int j = __ffs(qual) - 1;
         qual &= qual - 1;
         uint32_t hj = __shfl_sync(0xffffffffu, myhi, j);
         uint32_t ij = __shfl_sync(0xffffffffu, myid, j);
         if (cnt >= ef && hj >= worst_hi) continue;
-        if ((delmask >> j) & 1u) {  // admitted like any candidate, but queued instead of becoming a result
+        if (HASDEL && ((delmask >> j) & 1u)) {  // admitted like any candidate, but queued instead of becoming a result
           // (a tombstone whose visited status is only a guess is dropped: nothing else would keep it from
           //  being queued and expanded again and again once the visited table is full)
           if (!((unsure >> j) & 1u)) dq_push(c, dn, hj, ij, ovf);
@@ -699,7 +703,7 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
         if (PREFETCH && c.lane == 0) prefetch_l2(g.links0 + (size_t)ij * g.M0);
       }
     }
-    if (dn) {
+    if (HASDEL && dn) {
       // candidate_set.top(): the closer of (closest unexpanded result, closest queued tombstone)
       uint32_t dhi;
       const uint32_t dpos = dq_min(c, dn, dhi);
