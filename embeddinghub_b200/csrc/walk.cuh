@@ -328,9 +328,12 @@ __device__ __forceinline__ uint32_t ul_worst(const UList<KPL>& u) {
   for (int s = 1; s < KPL; ++s) m = max(m, u.hi[s]);
   return __reduce_max_sync(0xffffffffu, m);
 }
-#ifdef EHB_ULIST_V1  // A/B only: the round-1 form (one ballot + branch per slot)
 // Insert (hi, id) [warp-uniform]; cnt/worst_hi are maintained by the caller's copies.
 // Precondition when cnt == ef: hi < worst_hi.
+// (Round 2 tried a per-lane form — every lane reduces over its own KPL slots, then ONE ballot elects the
+//  lane, predicated writes select the slot — to cut the ~KPL dependent ballots per insert.  Measured on a
+//  B200 it lost everywhere: C5 shape 22.8 ms vs 9.0 ms (KPL = 8, 136 vs 128 registers), C3 shape 20.9 vs
+//  19.6 ms, C2 0.299 vs 0.293 ms; profiles/r02_ab_ulist.txt.  The slot-walking form below stays.)
 template <int KPL>
 __device__ __forceinline__ void ul_insert(UList<KPL>& u, uint32_t hi, uint32_t id, uint32_t ef, uint32_t& cnt,
                                           uint32_t& worst_hi, uint32_t lane) {
@@ -386,64 +389,6 @@ __device__ __forceinline__ uint32_t ul_min_unexpanded(UList<KPL>& u, bool mark, 
   }
   return node;
 }
-#else
-// Insert (hi, id) [warp-uniform]; cnt/worst_hi are maintained by the caller's copies.
-// Precondition when cnt == ef: hi < worst_hi (the true maximum over the occupied positions).
-// Each lane first reduces over its OWN KPL slots (which slot is free / holds my largest key), then ONE
-// ballot elects the lane: the cost is independent of KPL apart from register-local selects (v1 walked the
-// slots with one ballot + branch each: ~KPL dependent warp collectives per insert).
-template <int KPL>
-__device__ __forceinline__ void ul_insert(UList<KPL>& u, uint32_t hi, uint32_t id, uint32_t ef, uint32_t& cnt,
-                                          uint32_t& worst_hi, uint32_t lane) {
-  if (cnt < ef) {
-    int es = -1;  // my first free (valid, empty) slot
-#pragma unroll
-    for (int s = KPL - 1; s >= 0; --s)
-      if (u.id[s] == kInvalid && u.hi[s] == 0xFFFFFFFFu) es = s;
-    const uint32_t b = __ballot_sync(0xffffffffu, es >= 0);
-    if (b && (int)lane == __ffs(b) - 1) {
-#pragma unroll
-      for (int s = 0; s < KPL; ++s)
-        if (s == es) u.hi[s] = hi, u.id[s] = id;
-    }
-    cnt++;
-    if (cnt == ef) worst_hi = ul_worst<KPL>(u);
-  } else {
-    uint32_t m = 0;
-    int ms = -1;  // my slot holding the largest key among occupied slots
-#pragma unroll
-    for (int s = 0; s < KPL; ++s)
-      if (u.id[s] != kInvalid && (ms < 0 || u.hi[s] > m)) m = u.hi[s], ms = s;
-    const uint32_t b = __ballot_sync(0xffffffffu, ms >= 0 && m == worst_hi);
-    if (b && (int)lane == __ffs(b) - 1) {
-#pragma unroll
-      for (int s = 0; s < KPL; ++s)
-        if (s == ms) u.hi[s] = hi, u.id[s] = id;
-    }
-    worst_hi = ul_worst<KPL>(u);
-  }
-}
-// closest unexpanded entry: returns its id (flag clear) or kInvalid; mark=true sets its expanded flag
-template <int KPL>
-__device__ __forceinline__ uint32_t ul_min_unexpanded(UList<KPL>& u, bool mark, uint32_t lane) {
-  uint32_t m = 0xFFFFFFFFu, mid = kInvalid;
-  int ms = -1;  // my closest unexpanded slot (empty / dead slots carry the flag bit in kInvalid)
-#pragma unroll
-  for (int s = 0; s < KPL; ++s)
-    if (!(u.id[s] & kExpandedFlag) && (ms < 0 || u.hi[s] < m)) m = u.hi[s], mid = u.id[s], ms = s;
-  const uint32_t best = __reduce_min_sync(0xffffffffu, m);
-  const uint32_t b = __ballot_sync(0xffffffffu, ms >= 0 && m == best);
-  if (!b) return kInvalid;
-  const int l = __ffs(b) - 1;
-  const uint32_t node = __shfl_sync(0xffffffffu, mid, l);
-  if (mark && (int)lane == l) {
-#pragma unroll
-    for (int s = 0; s < KPL; ++s)
-      if (s == ms) u.id[s] |= kExpandedFlag;
-  }
-  return node;
-}
-#endif
 // ordered distance of the closest unexpanded entry (0xFFFFFFFF when there is none)
 template <int KPL>
 __device__ __forceinline__ uint32_t ul_min_unexpanded_hi(const UList<KPL>& u) {
