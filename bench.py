@@ -594,6 +594,18 @@ def run_ehb(args, wl):
 
         best, med, passes = timed_passes(one_pass, 5, 3, 40)
         cl = res["l"]
+        # hnswlib's own counters for the same graph and queries (metric_hops / metric_distance_computations):
+        # the roofline numerator WITHOUT anything the GPU walk adds (re-evaluations after a visited-table
+        # overflow, speculative expansions of the team walk)
+        o.metrics(reset=True)
+        one_pass()
+        om = o.metrics(reset=True)
+        clean_bytes = om["hops_upper"] * 4.0 * 16 + om["hops0"] * 8.0 * 16 + om["evals"] * 4.0 * d + Q * 4.0 * d
+        roofline["hnswlib_counters"] = {
+            "evals_per_query": om["evals"] / Q, "hops_per_query": om["hops0"] / Q,
+            "algorithmic_bytes_per_launch": clean_bytes,
+            "achieved": clean_bytes / (k_ms * 1e-3) / 1e9, "frac": clean_bytes / (k_ms * 1e-3) / 1e9 / peak,
+            "note": "same kernel duration, bytes from the oracle's counters on the same graph and queries"}
         t0c = time.perf_counter()
         o.search(qq[:max(Q // 20, 50)], k, ef=ef, threads=1)
         cpu_1t = max(Q // 20, 50) / (time.perf_counter() - t0c)
