@@ -211,7 +211,11 @@ def calibrate_threads(run, cores, sample_desc):
     """The CPU arm gets the thread count that serves it best on THIS box: a short sample is timed at
     nproc, nproc/2, ... (oversubscribed hyper-threads, NUMA and container CPU quotas make "all logical CPUs"
     the slowest choice on some hosts — round 1 saw 4.4x between two boxes).  run(threads) -> seconds."""
-    cand = sorted({c for c in (cores, cores // 2, cores // 4, cores // 8, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    lim = cgroup_cpu_limit()
+    cand = {cores, cores // 2, cores // 4, cores // 8, 32, 16, 8}
+    if lim:
+        cand |= {int(round(lim)), int(round(lim * 1.5)), int(round(lim * 2))}   # a CPU quota: stay near it
+    cand = sorted({c for c in cand if 1 <= c <= cores}, reverse=True)
     sweep = {}
     for c in cand:
         run(c)                      # warm
@@ -248,7 +252,7 @@ def oracle_build_prefix(orc, wl, budget_s, cores, cap, tune=None):
             built += m
             off += m
             if tune is not None and "threads" not in tune:
-                qs = gen(256, d, QUERY_SEED)
+                qs = gen(2048, d, QUERY_SEED)
                 t_cal = time.perf_counter()
 
                 def run(c):
@@ -256,7 +260,7 @@ def oracle_build_prefix(orc, wl, budget_s, cores, cap, tune=None):
                     o.search(qs, wl["k"], ef=wl["ef"], threads=c)
                     return time.perf_counter() - t1
 
-                threads, tune["sweep"] = calibrate_threads(run, cores, f"256 queries on the first {built} points")
+                threads, tune["sweep"] = calibrate_threads(run, cores, f"2048 queries on the first {built} points")
                 tune["threads"] = threads
                 t0 += time.perf_counter() - t_cal      # calibration is not construction time
         kept.append(x[:off])
@@ -584,10 +588,10 @@ def run_ehb(args, wl):
 
         def cal(c):
             t1 = time.perf_counter()
-            o.search(qq[:512], k, ef=ef, threads=c)
+            o.search(qq[:1024], k, ef=ef, threads=c)
             return time.perf_counter() - t1
 
-        cores, info["thread_sweep"] = calibrate_threads(cal, cores, f"512 of the {Q} queries on the full graph")
+        cores, info["thread_sweep"] = calibrate_threads(cal, cores, f"1024 of the {Q} queries on the full graph")
 
         def one_pass():
             res["l"] = o.search(qq, k, ef=ef, threads=cores)[0]
