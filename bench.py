@@ -347,6 +347,8 @@ def parity_block(ehb, orc, wl, budget_s, cores, device):
     t_gpu = time.perf_counter() - t0
     gt, _, _ = ix.search_bruteforce(q, k)
     ol, od, _ = o.search(q, k, ef=ef, threads=cores)
+    al, _, _ = ix.search(q, k, ef=ef)       # automatic warps per query (what a batch of this size gets)
+    ix.set_search_width(1)                  # one warp per query = hnswlib's expansion order: the identity check
     gl, gd, _ = ix.search(q, k, ef=ef)
     o2 = orc.OracleHNSW(d, metric, n1)
     o2.import_graph(ix.export_graph())
@@ -356,13 +358,15 @@ def parity_block(ehb, orc, wl, budget_s, cores, device):
     out = {"N_prime": n1, "queries": nq, "ef": ef, "k": k,
            "recall_oracle_built_oracle_walk": recall_at_k(ol, gt),
            "recall_gpu_built_gpu_walk": recall_at_k(gl, gt),
+           "recall_gpu_built_gpu_walk_auto_width": recall_at_k(al, gt),
            "recall_gpu_built_oracle_walk": recall_at_k(xl, gt),
            "ids_equal_gpu_vs_oracle_walk_same_graph": float(same.mean()),
            "max_rel_dist_err_same_graph": rel,
            "cpu_build_s": round(t_cpu, 1), "gpu_build_s": round(t_gpu, 2),
-           "gate": "recall(GPU) >= recall(oracle) at the same ef; |dist - oracle dist| <= 1e-4 relative"}
+           "gate": "recall(GPU) >= recall(oracle) - 0.005 at the same ef (two builds of the oracle itself differ by "
+                   "about that much); ids of the two walks on the same graph equal; |dist - oracle dist| <= 1e-4 relative"}
     out["gate_passed"] = bool(out["recall_gpu_built_gpu_walk"] >= out["recall_oracle_built_oracle_walk"] - 0.005 and
-                              (rel is None or rel <= 1e-4))
+                              out["ids_equal_gpu_vs_oracle_walk_same_graph"] >= 0.995 and (rel is None or rel <= 1e-4))
     del ix, o, o2
     return out
 
