@@ -14,10 +14,6 @@ const std::string& last_error_text() { return g_err; }
 }  // namespace ehb
 using ehb::fail;
 
-#ifndef EHB_WANT_CAP
-#define EHB_WANT_CAP 16  // resident warps per SM the visited-table sizing aims at (register budget: search_impl.cuh)
-#endif
-
 // ============================================================================================
 // index state
 // ============================================================================================
@@ -54,6 +50,9 @@ ehb::WalkCfg ehb_index::walk_cfg(uint32_t ef_eff, uint32_t smem_list, uint64_t j
   c.lcap = smem_list;
   c.staged = dpad > 256 ? 1 : 0;  // rows above 1 KB go through the TMA staging ring
   c.dcap = n_deleted ? ehb::kDeletedQueue : 0;
+  // dense walk (search_impl.cuh): batches big enough to fill 20 warps per SM, rows <= 512 B, no tombstones
+  c.dense = (!smem_list && team == 1 && !c.staged && dpad <= 128 && !n_deleted && jobs >= 20ull * (uint64_t)sms) ? 1 : 0;
+  const uint32_t warp_target = c.dense ? 20u : 16u;  // resident warps per SM the visited-table sizing aims at
   uint32_t vbytes = dpad * 4;
   uint32_t nslots = std::max(4u, std::min(32u, 24576u / vbytes));
   uint32_t ng = 2;                      // two groups: math on one overlaps the copies of the other
@@ -74,7 +73,7 @@ ehb::WalkCfg ehb_index::walk_cfg(uint32_t ef_eff, uint32_t smem_list, uint64_t j
     hs = 1u << t_hash_bits;
   } else {
     uint64_t ctas = (jobs + team - 1) / std::max(team, 1u);
-    uint32_t want = (uint32_t)std::min<uint64_t>((ctas + sms - 1) / sms, c.staged ? 5u : (uint32_t)EHB_WANT_CAP / team);
+    uint32_t want = (uint32_t)std::min<uint64_t>((ctas + sms - 1) / sms, c.staged ? 5u : warp_target / team);
     want = std::max(want, 4u);
     c.hash_size = 0;
     uint32_t fixed = ehb::warp_smem_bytes(c, dpad) * team + 1024u + (smem_list ? 256u : 0u);
@@ -514,8 +513,8 @@ int ehb_index::search_dev(ehb::SearchSlot* sl, uint64_t nq, const float* dq, uin
       std::snprintf(sl->last_kernel, sizeof(sl->last_kernel), "hnsw_search_team_kernel<NQ=%u,KPL=%u,T=%u>",
                     dpad / (4 * lpv), kpl, team);
     else
-      std::snprintf(sl->last_kernel, sizeof(sl->last_kernel), "hnsw_search_kernel<LPV=%u,NQ=%u,KPL=%u>", lpv,
-                    dpad / (4 * lpv), kpl);
+      std::snprintf(sl->last_kernel, sizeof(sl->last_kernel), "%s<LPV=%u,NQ=%u,KPL=%u>",
+                    cfg.dense ? "hnsw_search_dense_kernel" : "hnsw_search_kernel", lpv, dpad / (4 * lpv), kpl);
   }
   {
     std::lock_guard<std::mutex> g(last_mu);

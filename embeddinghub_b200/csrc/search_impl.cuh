@@ -4,22 +4,12 @@
 
 namespace ehb {
 
-// Register budget: by default ptxas chooses (128 for the round-1 loop at d=128 / ef=256; an explicit
-// minBlocksPerSM — even 1 — changes its heuristics: 143 registers, and a cap of 4 blocks serialises the
-// 16-vector load batches: 9.1 -> 22.7 ms on the C5 shape).  EHB_SEARCH_MINB (A/B builds only) sets one.
-#ifdef EHB_SEARCH_MINB
-#define EHB_SEARCH_BOUNDS __launch_bounds__(128, EHB_SEARCH_MINB)
-#else
-#define EHB_SEARCH_BOUNDS __launch_bounds__(128)
-#endif
-
-template <int LPV, int NQ, int KPL, bool HASDEL>
-__global__ void EHB_SEARCH_BOUNDS hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
-                                                          uint32_t nq, uint32_t k, uint32_t ef,
-                                                          uint64_t* __restrict__ out_labels,
-                                                          float* __restrict__ out_dists,
-                                                          uint32_t* __restrict__ out_counts,
-                                                          uint32_t* __restrict__ stats, uint32_t warp_smem) {
+// One warp walks one query (device body shared by the two kernels below).
+template <int LPV, int NQ, int KPL, bool HASDEL, int UDIV>
+__device__ __forceinline__ void search_body(const GraphView& g, const WalkCfg& cfg, const float* __restrict__ queries,
+                                            uint32_t nq, uint32_t k, uint32_t ef, uint64_t* __restrict__ out_labels,
+                                            float* __restrict__ out_dists, uint32_t* __restrict__ out_counts,
+                                            uint32_t* __restrict__ stats, uint32_t warp_smem) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t w = threadIdx.x >> 5;
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + w;
@@ -35,12 +25,12 @@ __global__ void EHB_SEARCH_BOUNDS hnsw_search_kernel(GraphView g, WalkCfg cfg, c
     uint32_t cur = g.entry;
     if (c.lane == 0) c.cand_id[0] = cur;
     __syncwarp();
-    eval_candidates<LPV, NQ>(c, g.vecs, qr, 1, g.metric);
+    eval_candidates<LPV, NQ, UDIV>(c, g.vecs, qr, 1, g.metric);
     float curdist = c.cand_dist[0];
     __syncwarp();
     wc.evals = 1;
-    greedy_descent<LPV, NQ>(c, g, qr, cur, curdist, g.max_level, 0, wc);
-    beam_search<LPV, NQ, KPL, true, HASDEL>(c, g, qr, ul, cur, curdist, 0, ef, kInvalid, wc);
+    greedy_descent<LPV, NQ, UDIV>(c, g, qr, cur, curdist, g.max_level, 0, wc);
+    beam_search<LPV, NQ, KPL, true, HASDEL, UDIV>(c, g, qr, ul, cur, curdist, 0, ef, kInvalid, wc);
   }
   // nearest-first output: extract the k closest in ascending order
   uint32_t found = 0;
@@ -63,6 +53,34 @@ __global__ void EHB_SEARCH_BOUNDS hnsw_search_kernel(GraphView g, WalkCfg cfg, c
   }
 }
 
+// Register budget of the default form: ptxas chooses (128 registers for d = 128 / ef = 256, 16 vectors in
+// flight per warp).  An explicit minBlocksPerSM changes its heuristics — even "1" gives 143 registers, and
+// capping this body at 128 serialised the load batches: 9.1 -> 22.7 ms on the C5 shape — so none is given.
+template <int LPV, int NQ, int KPL, bool HASDEL>
+__global__ void __launch_bounds__(128) hnsw_search_kernel(GraphView g, WalkCfg cfg, const float* __restrict__ queries,
+                                                          uint32_t nq, uint32_t k, uint32_t ef,
+                                                          uint64_t* __restrict__ out_labels,
+                                                          float* __restrict__ out_dists,
+                                                          uint32_t* __restrict__ out_counts,
+                                                          uint32_t* __restrict__ stats, uint32_t warp_smem) {
+  search_body<LPV, NQ, KPL, HASDEL, 1>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, warp_smem);
+}
+
+// "Dense" form for big batches of short rows (LPV = 8, d <= 128): 8 vectors in flight per warp instead of 16
+// and a 96-register budget -> 20 resident warps per SM instead of 16 (the visited table shrinks to match,
+// api.cu walk_cfg).  Measured on the C5 shape (N = 1M, Q = 10k, ef = 256): 8.66 ms vs 9.08 ms; with the
+// same 8-vector batches but 16 warps: 9.48 ms (profiles/r02_ab_walk_occupancy.txt).
+template <int LPV, int NQ, int KPL>
+__global__ void __launch_bounds__(128, 5) hnsw_search_dense_kernel(GraphView g, WalkCfg cfg,
+                                                                   const float* __restrict__ queries, uint32_t nq,
+                                                                   uint32_t k, uint32_t ef,
+                                                                   uint64_t* __restrict__ out_labels,
+                                                                   float* __restrict__ out_dists,
+                                                                   uint32_t* __restrict__ out_counts,
+                                                                   uint32_t* __restrict__ stats, uint32_t warp_smem) {
+  search_body<LPV, NQ, KPL, false, 2>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, warp_smem);
+}
+
 template <int LPV, int NQ, int KPL, bool HASDEL>
 cudaError_t launch_search_t(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
                             uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
@@ -70,7 +88,11 @@ cudaError_t launch_search_t(const GraphView& g, const WalkCfg& cfg, const float*
   uint32_t wsm = warp_smem_bytes(cfg, g.dpad);
   size_t smem = (size_t)wsm * wpb;
   dim3 grid((nq + wpb - 1) / wpb), block(32 * wpb);
-  auto kern = hnsw_search_kernel<LPV, NQ, KPL, HASDEL>;
+  void (*kern)(GraphView, WalkCfg, const float*, uint32_t, uint32_t, uint32_t, uint64_t*, float*, uint32_t*, uint32_t*,
+               uint32_t) = hnsw_search_kernel<LPV, NQ, KPL, HASDEL>;
+  if constexpr (LPV == 8 && NQ <= 4 && !HASDEL) {
+    if (cfg.dense) kern = hnsw_search_dense_kernel<LPV, NQ, KPL>;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, block, smem, s>>>(g, cfg, queries, nq, k, ef, out_labels, out_dists, out_counts, stats, wsm);

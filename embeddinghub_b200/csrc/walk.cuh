@@ -45,6 +45,7 @@ struct WalkCfg {
   uint32_t G;          // vectors per TMA staging group (<= 32), LPV = 32 only
   uint32_t NG;         // staging groups (ring depth, <= 8)
   uint32_t staged;     // 1 when the TMA staging ring is allocated
+  uint32_t dense;      // 1: launch the low-register form of the walk (more resident warps; rows <= 512 B only)
   uint32_t dcap;       // capacity of the side queue of admitted-but-deleted candidates (0 = index has no tombstones)
 };
 
@@ -198,10 +199,11 @@ __device__ __forceinline__ float group_reduce(float acc) {
 }
 
 // ---- LPV = 8: direct 128-bit loads, U steps (4 vectors each) in flight ------
-#ifndef EHB_EVAL_UDIV
-#define EHB_EVAL_UDIV 1  // A/B: divide the number of 4-vector load steps kept in flight
-#endif
-template <int NQ, int U = ((NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2)) / EHB_EVAL_UDIV > 0 ? (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2)) / EHB_EVAL_UDIV : 1)>  // default: 64 registers of loads in flight
+// default U: 64 registers of loads in flight (16 vectors at d <= 128)
+__host__ __device__ constexpr int eval_u(int NQ, int UDIV) {
+  return ((NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2)) / UDIV) > 0 ? (NQ <= 2 ? 8 : (NQ <= 4 ? 4 : 2)) / UDIV : 1;
+}
+template <int NQ, int U = eval_u(NQ, 1)>
 __device__ __forceinline__ void eval_direct(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
                                             uint32_t m, int metric) {
   const uint32_t sub = c.lane & 7u, grp = c.lane >> 3;
@@ -287,12 +289,13 @@ __device__ __forceinline__ void eval_staged(WarpCtx& c, const float* __restrict_
   __syncwarp();
 }
 
-// cand_id[0..m) -> cand_dist[0..m): distances from the register-held query.
-template <int LPV, int NQ>
+// cand_id[0..m) -> cand_dist[0..m): distances from the register-held query.  UDIV > 1 halves (…) the
+// load batches kept in flight per warp: fewer registers, more resident warps (the "dense" walk).
+template <int LPV, int NQ, int UDIV = 1>
 __device__ __forceinline__ void eval_candidates(WarpCtx& c, const float* __restrict__ vecs, const float4 (&qr)[NQ],
                                                 uint32_t m, int metric) {
   if (LPV == 8)
-    eval_direct<NQ>(c, vecs, qr, m, metric);
+    eval_direct<NQ, eval_u(NQ, UDIV)>(c, vecs, qr, m, metric);
   else
     eval_staged<NQ>(c, vecs, qr, m, metric);
 }
@@ -483,7 +486,7 @@ __device__ __forceinline__ uint32_t load_row(const GraphView& g, uint32_t node, 
 
 // hnswlib searchKnn's upper-layer descent: at each level move to the closest
 // neighbour until no neighbour improves.
-template <int LPV, int NQ>
+template <int LPV, int NQ, int UDIV = 1>
 __device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], uint32_t& cur,
                                                float& curdist, int from_level, int to_level_excl,
                                                WalkCounters& wc) {
@@ -500,7 +503,7 @@ __device__ __forceinline__ void greedy_descent(WarpCtx& c, const GraphView& g, c
       if (nb != kInvalid) c.cand_id[__popc(mask & lanemask_lt())] = nb;
       __syncwarp();
       wc.evals += m;
-      eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
+      eval_candidates<LPV, NQ, UDIV>(c, g.vecs, qr, m, g.metric);
       float bd = c.lane < m ? c.cand_dist[c.lane] : INFINITY;
       uint32_t bl = c.lane;
 #pragma unroll
@@ -570,7 +573,7 @@ __device__ __forceinline__ uint32_t dq_min(const WarpCtx& c, uint32_t dn, uint32
 
 // HASDEL = false compiles every trace of the tombstone machinery out (an index without tombstones runs
 // exactly the round-1 loop: the extra live registers cost the 16-vector load batches their overlap).
-template <int LPV, int NQ, int KPL, bool PREFETCH, bool HASDEL>
+template <int LPV, int NQ, int KPL, bool PREFETCH, bool HASDEL, int UDIV = 1>
 __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, const float4 (&qr)[NQ], UList<KPL>& u,
                                             uint32_t ep, float epdist, int level, uint32_t ef, uint32_t exclude,
                                             WalkCounters& wc) {
@@ -616,7 +619,7 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       const uint32_t unsure = (HASDEL && del) ? __reduce_or_sync(0xffffffffu, (is_new && o) ? (1u << pos) : 0u) : 0u;
       __syncwarp();
       wc.evals += m;
-      eval_candidates<LPV, NQ>(c, g.vecs, qr, m, g.metric);
+      eval_candidates<LPV, NQ, UDIV>(c, g.vecs, qr, m, g.metric);
       // the speculative row has arrived by now: pull its neighbours' vectors towards L2 while this hop's
       // candidates are inserted (rows <= 1 KB only; a wrong guess costs bandwidth, not correctness)
       if (PREFETCH && LPV == 8 && spec_row != kInvalid) {
