@@ -45,7 +45,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 
 // One persistent launch per rank and step; grid <= resident capacity so no CTA waits on an unscheduled one.
-__global__ void __launch_bounds__(256) exchange_merge_kernel(ExchangeView ev, uint32_t parity, uint32_t epoch,
+// 1024 threads per CTA: the push is a plain copy and the merge is one latency-bound warp per query, so both
+// want as many warps per SM as one resident CTA can hold.
+constexpr uint32_t kExchangeThreads = 1024;
+__global__ void __launch_bounds__(kExchangeThreads) exchange_merge_kernel(ExchangeView ev, uint32_t parity, uint32_t epoch,
                                                              uint64_t nq, uint32_t k, uint32_t qs, uint32_t nslices,
                                                              float* __restrict__ out_dists,
                                                              uint64_t* __restrict__ out_labels,
@@ -248,7 +251,7 @@ int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out
   qs = (qs + 3) / 4 * 4;
   uint32_t nslices = (uint32_t)((nq + qs - 1) / qs);
   uint32_t grid = std::min<uint32_t>(nslices, (uint32_t)ex->sms);
-  ehb::exchange_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ev, ex->epoch & 1u, ex->epoch, nq, k, qs, nslices,
+  ehb::exchange_merge_kernel<<<grid, ehb::kExchangeThreads, 0, (cudaStream_t)stream>>>(ev, ex->epoch & 1u, ex->epoch, nq, k, qs, nslices,
                                                                      out_dists_dev, out_labels_dev, out_counts_dev,
                                                                      (uint32_t*)(ex->local + ex->flag_bytes - 4));
   CU(cudaGetLastError());
