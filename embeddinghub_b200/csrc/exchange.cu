@@ -115,6 +115,7 @@ struct ehb_exchange {
   unsigned char* mapped[ehb::kMaxWorld] = {nullptr};  // base of every rank's allocation as mapped here
   bool opened[ehb::kMaxWorld] = {false};
   bool attached = false;
+  uint32_t same_device_ranks = 1;  // ranks (this one included) whose exchange kernels share this GPU (tests)
   uint32_t epoch = 0;
   uint64_t slot_nq = 0;
   uint32_t slot_k = 0;
@@ -204,6 +205,7 @@ int ehb_exchange_attach_local(ehb_exchange* ex, uint32_t peer_rank, ehb_exchange
     if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
     cudaGetLastError();
   }
+  if (!ex->mapped[peer_rank] && peer->device == ex->device) ex->same_device_ranks++;
   ex->mapped[peer_rank] = peer->local;
   bool all = true;
   for (uint32_t g = 0; g < ex->world; ++g) all = all && ex->mapped[g] != nullptr;
@@ -250,7 +252,9 @@ int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out
   uint32_t qs = (uint32_t)((nq + target - 1) / target);
   qs = (qs + 3) / 4 * 4;
   uint32_t nslices = (uint32_t)((nq + qs - 1) / qs);
-  uint32_t grid = std::min<uint32_t>(nslices, (uint32_t)ex->sms);
+  // every CTA must be resident (a waiting CTA may depend on a peer's CTA): one CTA per SM, and when several ranks
+  // share this GPU (single-GPU tests) they split the SMs
+  uint32_t grid = std::min<uint32_t>(nslices, std::max<uint32_t>(1, (uint32_t)ex->sms / ex->same_device_ranks));
   ehb::exchange_merge_kernel<<<grid, ehb::kExchangeThreads, 0, (cudaStream_t)stream>>>(ev, ex->epoch & 1u, ex->epoch, nq, k, qs, nslices,
                                                                      out_dists_dev, out_labels_dev, out_counts_dev,
                                                                      (uint32_t*)(ex->local + ex->flag_bytes - 4));
