@@ -204,7 +204,8 @@ int ehb_index_set_tuning(ehb_index* ix, uint32_t stage_slots, uint32_t stage_gro
  * One process drives n_dev devices: labels [i*span, (i+1)*span) live on shard i % n_dev (span 0: label %
  * n_dev); every shard owns an independent graph; a search runs on every shard, whose kernels store their
  * top-k straight into device_ids[0]'s gather buffer over NVLink (peer access), and one merge kernel there
- * produces the result.  No collective on either path.  Same conventions as the single-index calls. */
+ * produces the result.  No collective on either path.  Same conventions as the single-index calls; calls on one
+ * ehb_sharded handle are serialised (one gather buffer per handle). */
 typedef struct ehb_sharded ehb_sharded; /* opaque */
 int ehb_sharded_create(const ehb_params* p /* device ignored; capacity per shard */, const int32_t* device_ids,
                        uint32_t n_dev, uint64_t shard_span, ehb_sharded** out);
