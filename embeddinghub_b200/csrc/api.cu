@@ -478,7 +478,8 @@ void ehb_index::release_slot(ehb::SearchSlot* sl, cudaStream_t used) {
 // ---- search --------------------------------------------------------------------------------------------
 // Caller holds the shared lock, the graph is built, `sl` is acquired.
 int ehb_index::search_dev(ehb::SearchSlot* sl, uint64_t nq, const float* dq, uint32_t k, uint32_t ef_in, uint64_t* dl,
-                          float* dd, uint32_t* dc, cudaStream_t s) {
+                          float* dd, uint32_t* dc, cudaStream_t s, const ehb::ResultSink* sink, bool* pushed) {
+  if (pushed) *pushed = false;
   if (k == 0 || nq == 0) return EHB_OK;
   uint32_t ef_eff = std::max(ef_in ? ef_in : ef, k);
   if (ef_eff > ehb::kMaxEf) return fail(EHB_ERR_INVALID, "max(ef, k) must be <= 512");
@@ -502,8 +503,19 @@ int ehb_index::search_dev(ehb::SearchSlot* sl, uint64_t nq, const float* dq, uin
   CU(cudaEventRecord(sl->ev0, s));
   if (team >= 2)
     CU(ehb::launch_search_team(team, view(), cfg.hash_size, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, sl->stats.p, s));
-  else
-    CU(ehb::launch_search(view(), cfg, q, (uint32_t)nq, k, ef_eff, dl, dd, dc, sl->stats.p, wpb, s));
+  else {
+    ehb::ResultSink one;
+    if (!sink) {
+      std::memset(&one, 0, sizeof(one));
+      one.labels[0] = dl;
+      one.dists[0] = dd;
+      one.n = 1;
+      sink = &one;
+    } else if (pushed) {
+      *pushed = true;
+    }
+    CU(ehb::launch_search(view(), cfg, q, (uint32_t)nq, k, ef_eff, *sink, dc, sl->stats.p, wpb, s));
+  }
   CU(cudaEventRecord(sl->ev1, s));
   sl->last_nq = nq;
   {
@@ -872,6 +884,24 @@ int ehb_index_search_dev(ehb_index* ix, uint64_t nq, const float* dq, uint32_t k
   ix->release_slot(sl, s);
   return rc;
 }
+
+}  // extern "C"
+
+int ehb_index_search_dev_sink(ehb_index* ix, uint64_t nq, const float* dq, uint32_t k, uint32_t ef,
+                              const ehb::ResultSink* sink, uint32_t* dc, cudaStream_t stream, bool* pushed) {
+  ENTER_S(ix);
+  if (!dq || !sink || !sink->n || !sink->labels[0]) return fail(EHB_ERR_INVALID, "null buffer");
+  if (k == 0 || nq == 0) return EHB_OK;
+  RET(ix->ensure_built(_g));
+  ehb::SearchSlot* sl = nullptr;
+  RET(ix->acquire_slot(&sl));
+  cudaStream_t s = stream ? stream : sl->stream;
+  int rc = ix->search_dev(sl, nq, dq, k, ef, sink->labels[0], sink->dists[0], dc, s, sink, pushed);
+  ix->release_slot(sl, s);
+  return rc;
+}
+
+extern "C" {
 
 int ehb_index_search_bruteforce(ehb_index* ix, uint64_t nq, const float* q, uint32_t k, int precision, uint64_t* ol,
                                 float* od, uint32_t* oc) {

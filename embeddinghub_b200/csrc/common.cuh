@@ -75,6 +75,16 @@ __device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
   return v;
 }
 
+// system-scope release / acquire on a flag word (peer memory over NVLink)
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;

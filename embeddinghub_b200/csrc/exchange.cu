@@ -35,15 +35,6 @@ struct ExchangeView {
   uint64_t stride;                 // bytes per rank block
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // One persistent launch per rank and step; grid <= resident capacity so no CTA waits on an unscheduled one.
 // 1024 threads per CTA: the push is a plain copy and the merge is one latency-bound warp per query, so both
 // want as many warps per SM as one resident CTA can hold.
@@ -53,13 +44,15 @@ __global__ void __launch_bounds__(kExchangeThreads) exchange_merge_kernel(Exchan
                                                              float* __restrict__ out_dists,
                                                              uint64_t* __restrict__ out_labels,
                                                              uint32_t* __restrict__ out_counts,
-                                                             uint32_t* __restrict__ timeout_flag) {
+                                                             uint32_t* __restrict__ timeout_flag, uint32_t skip_push) {
   const uint32_t W = ev.world, me = ev.rank;
   const uint64_t blk = ((uint64_t)parity * W + me) * ev.stride;  // my block inside ANY rank's buffer
   const unsigned char* mine = ev.recv[me] + blk;                 // written by my search kernels
   const uint64_t lab_bytes = nq * k * 8ull;
   // ---- phase 1: push my slices to every peer, then raise their flags ------------------------------------
-  for (uint32_t s = blockIdx.x; s < nslices; s += gridDim.x) {
+  // (skipped when the producer was the one-warp walk: its epilogue already stored every query's results into
+  //  the peers' buffers and raised the slice flags — search_impl.cuh)
+  for (uint32_t s = blockIdx.x; s < nslices && !skip_push; s += gridDim.x) {
     const uint64_t q0 = (uint64_t)s * qs, q1 = min(nq, q0 + qs);
     const uint64_t e0 = q0 * k, e1 = q1 * k;  // element range of the slice
     const uint64_t* src_l = (const uint64_t*)mine;
@@ -115,6 +108,7 @@ struct ehb_exchange {
   unsigned char* mapped[ehb::kMaxWorld] = {nullptr};  // base of every rank's allocation as mapped here
   bool opened[ehb::kMaxWorld] = {false};
   bool attached = false;
+  uint32_t* slice_count = nullptr;  // [kMaxSlices], zero between steps (raised by the walk's epilogue)
   uint32_t same_device_ranks = 1;  // ranks (this one included) whose exchange kernels share this GPU (tests)
   uint32_t epoch = 0;
   uint64_t slot_nq = 0;
@@ -143,7 +137,10 @@ int ehb_exchange_create(int32_t device, uint32_t world, uint32_t rank, uint64_t 
   cudaDeviceGetAttribute(&ex->sms, cudaDevAttrMultiProcessorCount, device);
   cudaError_t e = cudaMalloc((void**)&ex->local, ex->total_bytes);
   if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->flag_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ex->slice_count, ehb::kMaxSlices * 4);
+  if (e == cudaSuccess) e = cudaMemset(ex->slice_count, 0, ehb::kMaxSlices * 4);
   if (e != cudaSuccess) {
+    if (ex->slice_count) cudaFree(ex->slice_count);
     if (ex->local) cudaFree(ex->local);
     delete ex;
     return fail(e == cudaErrorMemoryAllocation ? EHB_ERR_OOM : EHB_ERR_CUDA, cudaGetErrorString(e));
@@ -160,6 +157,7 @@ int ehb_exchange_destroy(ehb_exchange* ex) {
   cudaDeviceSynchronize();
   for (uint32_t g = 0; g < ex->world; ++g)
     if (ex->opened[g]) cudaIpcCloseMemHandle(ex->mapped[g]);
+  if (ex->slice_count) cudaFree(ex->slice_count);
   if (ex->local) cudaFree(ex->local);
   delete ex;
   return EHB_OK;
@@ -229,15 +227,21 @@ int ehb_exchange_begin(ehb_exchange* ex, uint64_t nq, uint32_t k, uint64_t** lab
   return EHB_OK;
 }
 
-// Finishes the step on `stream` (the stream the search was queued on): push + flags + wait + merge.
-int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev,
-                           void* stream) {
-  if (!ex || !out_labels_dev) return fail(EHB_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(ex->device));
-  std::lock_guard<std::mutex> g(ex->mu);
-  if (!ex->slot_nq) return fail(EHB_ERR_STATE, "ehb_exchange_begin was not called");
-  const uint64_t nq = ex->slot_nq;
-  const uint32_t k = ex->slot_k;
+}  // extern "C"
+
+namespace {
+
+// slices of whole queries, a multiple of 4 queries so every slice boundary is 16 B aligned
+void slice_plan(const ehb_exchange* ex, uint64_t nq, uint32_t* qs, uint32_t* nslices) {
+  uint32_t target = std::min<uint32_t>(ehb::kMaxSlices, (uint32_t)ex->sms);
+  uint32_t per = (uint32_t)((nq + target - 1) / target);
+  per = (per + 3) / 4 * 4;
+  *qs = per;
+  *nslices = (uint32_t)((nq + per - 1) / per);
+}
+
+int launch_exchange_merge(ehb_exchange* ex, uint64_t nq, uint32_t k, float* out_dists_dev, uint64_t* out_labels_dev,
+                          uint32_t* out_counts_dev, cudaStream_t stream, bool skip_push) {
   ehb::ExchangeView ev;
   std::memset(&ev, 0, sizeof(ev));
   for (uint32_t r = 0; r < ex->world; ++r) {
@@ -247,20 +251,73 @@ int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out
   ev.world = ex->world;
   ev.rank = ex->rank;
   ev.stride = ex->stride;
-  // slices of whole queries, a multiple of 4 queries so every slice boundary is 16 B aligned
-  uint32_t target = std::min<uint32_t>(ehb::kMaxSlices, (uint32_t)ex->sms);
-  uint32_t qs = (uint32_t)((nq + target - 1) / target);
-  qs = (qs + 3) / 4 * 4;
-  uint32_t nslices = (uint32_t)((nq + qs - 1) / qs);
+  uint32_t qs, nslices;
+  slice_plan(ex, nq, &qs, &nslices);
   // every CTA must be resident (a waiting CTA may depend on a peer's CTA): one CTA per SM, and when several ranks
   // share this GPU (single-GPU tests) they split the SMs
   uint32_t grid = std::min<uint32_t>(nslices, std::max<uint32_t>(1, (uint32_t)ex->sms / ex->same_device_ranks));
-  ehb::exchange_merge_kernel<<<grid, ehb::kExchangeThreads, 0, (cudaStream_t)stream>>>(ev, ex->epoch & 1u, ex->epoch, nq, k, qs, nslices,
-                                                                     out_dists_dev, out_labels_dev, out_counts_dev,
-                                                                     (uint32_t*)(ex->local + ex->flag_bytes - 4));
+  ehb::exchange_merge_kernel<<<grid, ehb::kExchangeThreads, 0, stream>>>(
+      ev, ex->epoch & 1u, ex->epoch, nq, k, qs, nslices, out_dists_dev, out_labels_dev, out_counts_dev,
+      (uint32_t*)(ex->local + ex->flag_bytes - 4), skip_push ? 1u : 0u);
   CU(cudaGetLastError());
-  ex->slot_nq = 0;
   return EHB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Finishes the step on `stream` (the stream the search was queued on): push + flags + wait + merge.
+int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev,
+                           void* stream) {
+  if (!ex || !out_labels_dev) return fail(EHB_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(ex->device));
+  std::lock_guard<std::mutex> g(ex->mu);
+  if (!ex->slot_nq) return fail(EHB_ERR_STATE, "ehb_exchange_begin was not called");
+  const uint64_t nq = ex->slot_nq;
+  const uint32_t k = ex->slot_k;
+  ex->slot_nq = 0;
+  return launch_exchange_merge(ex, nq, k, out_dists_dev, out_labels_dev, out_counts_dev, (cudaStream_t)stream, false);
+}
+
+// One sharded graph search step, fused: this rank's walk stores every query's top-k straight into every peer's
+// receive buffer from its epilogue (coalesced stores over NVLink while the other queries are still walking) and
+// raises per-slice flags; then one kernel waits for the peers' flags and merges.  Falls back to push-after-walk
+// when the batch is small enough for the team walk.  Call in lock step on every rank.
+int ehb_exchange_search_dev(ehb_exchange* ex, ehb_index* ix, uint64_t nq, const float* queries_dev, uint32_t k,
+                            uint32_t ef, float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev,
+                            uint32_t* shard_counts_dev, void* stream) {
+  if (!ex || !ix || !queries_dev || !out_labels_dev) return fail(EHB_ERR_INVALID, "null argument");
+  if (nq == 0 || k == 0 || nq * k > ex->max_elems) return fail(EHB_ERR_INVALID, "nq * k exceeds the exchange capacity");
+  if (!ex->attached) return fail(EHB_ERR_STATE, "peers are not attached yet");
+  CU(cudaSetDevice(ex->device));
+  std::lock_guard<std::mutex> g(ex->mu);
+  ex->epoch++;
+  const uint32_t parity = ex->epoch & 1u, W = ex->world, me = ex->rank;
+  const uint64_t blk = ((uint64_t)parity * W + me) * ex->stride;
+  uint32_t qs, nslices;
+  slice_plan(ex, nq, &qs, &nslices);
+  ehb::ResultSink sink;
+  std::memset(&sink, 0, sizeof(sink));
+  uint32_t t = 0;
+  auto add = [&](uint32_t r) {
+    unsigned char* base = ex->mapped[r] + ex->flag_bytes + blk;
+    sink.labels[t] = (uint64_t*)base;
+    sink.dists[t] = (float*)(base + nq * k * 8ull);
+    sink.flags[t] = (uint32_t*)ex->mapped[r] + ((uint64_t)parity * W + me) * ehb::kMaxSlices;
+    ++t;
+  };
+  add(me);  // destination 0 = my own block of my own buffer
+  for (uint32_t r = 0; r < W; ++r)
+    if (r != me) add(r);
+  sink.n = t;
+  sink.qs = qs;
+  sink.epoch = ex->epoch;
+  sink.slice_count = ex->slice_count;
+  bool pushed = false;
+  RET(ehb_index_search_dev_sink(ix, nq, queries_dev, k, ef, &sink, shard_counts_dev, (cudaStream_t)stream, &pushed));
+  CU(cudaSetDevice(ex->device));
+  return launch_exchange_merge(ex, nq, k, out_dists_dev, out_labels_dev, out_counts_dev, (cudaStream_t)stream, pushed);
 }
 
 // 1 when some exchange kernel of this rank gave up waiting for a peer (its results are then invalid).

@@ -188,6 +188,10 @@ constexpr uint32_t kDeletedQueue = 64;     // side queue of tombstoned candidate
 
 }  // namespace ehb
 
+// ehb_index_search_dev with a result sink (exchange.cu)
+int ehb_index_search_dev_sink(ehb_index* ix, uint64_t nq, const float* dq, uint32_t k, uint32_t ef,
+                              const ehb::ResultSink* sink, uint32_t* dc, cudaStream_t stream, bool* pushed);
+
 struct ehb_index {
   ehb_params prm;
   uint32_t dim, dpad, M, M0;
@@ -282,8 +286,10 @@ struct ehb_index {
   int ensure_built(std::shared_lock<ehb::RwLock>& lk);
   int acquire_slot(ehb::SearchSlot** out);
   void release_slot(ehb::SearchSlot* sl, cudaStream_t used);
+  // sink (optional): extra destinations + slice flags for the sharded exchange; *pushed tells whether the
+  // launched kernel honoured it (the one-warp walk does, the team walk does not)
   int search_dev(ehb::SearchSlot* sl, uint64_t nq, const float* dq, uint32_t k, uint32_t ef_in, uint64_t* dl, float* dd,
-                 uint32_t* dc, cudaStream_t s);
+                 uint32_t* dc, cudaStream_t s, const ehb::ResultSink* sink = nullptr, bool* pushed = nullptr);
   int bruteforce_dev(uint64_t nq, const float* dq, uint32_t k, int precision, uint64_t* dl, float* dd, uint32_t* dc,
                      cudaStream_t s);
   void reset_content();

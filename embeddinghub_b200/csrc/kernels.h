@@ -14,8 +14,8 @@ constexpr uint32_t kUpdCandCap = 1088;  // update path: sCand capacity per moved
 // K2 — batched k-NN graph walk (hnswlib searchKnn).  ef >= k, cfg.lcap >= ef.
 // stats: [nq][4] u32 = hops_upper, hops_base, evals, overflow.
 cudaError_t launch_search(const GraphView& g, const WalkCfg& cfg, const float* queries, uint32_t nq, uint32_t k,
-                          uint32_t ef, uint64_t* out_labels, float* out_dists, uint32_t* out_counts,
-                          uint32_t* stats, uint32_t warps_per_block, cudaStream_t s);
+                          uint32_t ef, const ResultSink& sink, uint32_t* out_counts, uint32_t* stats,
+                          uint32_t warps_per_block, cudaStream_t s);
 
 // K2t — team walk (T warps per query, T in {2,4}); rows <= 1 KB and ef <= 256 only.
 cudaError_t launch_search_team(uint32_t T, const GraphView& g, uint32_t hash_size, const float* queries, uint32_t nq,

@@ -49,6 +49,20 @@ struct WalkCfg {
   uint32_t dcap;       // capacity of the side queue of admitted-but-deleted candidates (0 = index has no tombstones)
 };
 
+// Where a walk writes its [nq][k] results.  Destination 0 is local; in a sharded deployment the others are
+// THIS rank's block inside every peer's receive buffer (CUDA-IPC / peer mappings): the walk's epilogue stores
+// the results of each query to all of them with coalesced stores over NVLink, and the warp that completes a
+// slice of `qs` queries raises that slice's flag on every peer (st.release.sys) — the transfer overlaps the
+// rest of the walk, and the merge kernel (exchange.cu) only waits on flags.
+constexpr uint32_t kMaxSinks = 16;
+struct ResultSink {
+  uint64_t* labels[kMaxSinks];
+  float* dists[kMaxSinks];     // all null or none
+  uint32_t* flags[kMaxSinks];  // [slices] of (parity, this rank) on destination t; unused for t = 0
+  uint32_t* slice_count;       // local [slices], zero between steps
+  uint32_t n, qs, epoch;       // destinations; queries per slice (0: no flags); value the flags take
+};
+
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // Supported padded row lengths: LPV=8 -> NQ in {1,2,4,8}; LPV=32 -> NQ in {3,4,6,8,12,16}.

@@ -134,6 +134,14 @@ class ShardedSearcher:
             return b["l"], b["d"], b["c"]
         if self.exchange == "peer":
             self._ensure_exchange(nq, k)
+            if not bruteforce:
+                # fused: the walk's epilogue stores each query's top-k into every peer's receive buffer and raises
+                # the slice flags; one kernel waits for the peers' flags and merges
+                check(lib().ehb_exchange_search_dev(self._ex, self.ix._h, nq, C.c_void_p(q.data_ptr()), k, ef,
+                                                    C.c_void_p(b["md"].data_ptr()), C.c_void_p(b["ml"].data_ptr()),
+                                                    C.c_void_p(b["mc"].data_ptr()), C.c_void_p(b["c"].data_ptr()),
+                                                    C.c_void_p(stream_ptr)))
+                return b["ml"], b["md"], b["mc"]
             lp, dp = C.c_void_p(), C.c_void_p()
             check(lib().ehb_exchange_begin(self._ex, nq, k, C.byref(lp), C.byref(dp)))
             # the shard's kernels write straight into this rank's block of its own receive buffer ...

@@ -241,6 +241,13 @@ int ehb_exchange_attach_local(ehb_exchange* ex, uint32_t peer_rank, ehb_exchange
 int ehb_exchange_begin(ehb_exchange* ex, uint64_t nq, uint32_t k, uint64_t** labels_dev, float** dists_dev);
 int ehb_exchange_merge_dev(ehb_exchange* ex, float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev,
                            void* stream);
+/* The fused step for graph searches (replaces begin + ehb_index_search_dev + merge_dev): the walk kernel's
+ * epilogue stores each query's top-k into every peer's receive buffer (coalesced stores over NVLink, overlapping
+ * the rest of the walk) and raises per-slice flags; one kernel then waits for the peers' flags and merges.
+ * shard_counts_dev ([nq], this shard's hit counts) may be NULL. */
+int ehb_exchange_search_dev(ehb_exchange* ex, ehb_index* ix, uint64_t nq, const float* queries_dev, uint32_t k,
+                            uint32_t ef, float* out_dists_dev, uint64_t* out_labels_dev, uint32_t* out_counts_dev,
+                            uint32_t* shard_counts_dev, void* stream);
 int ehb_exchange_timed_out(ehb_exchange* ex, uint32_t* out /* 1: a wait for a peer gave up (~20 s) */);
 
 /* Named integer options (A/B switches and construction knobs that are not part of

@@ -403,5 +403,56 @@ def test_exchange_two_ranks_in_one_process():
             t = C.c_uint32()
             check(L.ehb_exchange_timed_out(exs[r], C.byref(t)))
             assert t.value == 0
+    # graph search: the fused step (walk epilogue stores into the peers' buffers + slice flags, merge waits) must
+    # give exactly what push-after-walk gives
+    def run(fused):
+        res, streams = [], []
+        for r in range(2):
+            torch.cuda.set_device(devs[r])
+            s = torch.cuda.Stream(device=devs[r])
+            streams.append(s)
+            dev = f"cuda:{devs[r]}"
+            dq = torch.from_numpy(q).to(dev)
+            ml = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            md = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            mc = torch.empty(nq, dtype=torch.int32, device=dev)
+            cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+            res.append((ml, md, mc, dq, cnt))
+            if not fused:
+                lp, dp = C.c_void_p(), C.c_void_p()
+                check(L.ehb_exchange_begin(exs[r], nq, k, C.byref(lp), C.byref(dp)))
+                ixs[r].search_dev(dq.data_ptr(), nq, k, 64, lp.value, dp.value, cnt.data_ptr(), s.cuda_stream)
+        for r in range(2):
+            torch.cuda.set_device(devs[r])
+            ml, md, mc, dq, cnt = res[r]
+            if fused:
+                check(L.ehb_exchange_search_dev(exs[r], ixs[r]._h, nq, C.c_void_p(dq.data_ptr()), k, 64,
+                                                C.c_void_p(md.data_ptr()), C.c_void_p(ml.data_ptr()),
+                                                C.c_void_p(mc.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                C.c_void_p(streams[r].cuda_stream)))
+            else:
+                check(L.ehb_exchange_merge_dev(exs[r], C.c_void_p(md.data_ptr()), C.c_void_p(ml.data_ptr()),
+                                               C.c_void_p(mc.data_ptr()), C.c_void_p(streams[r].cuda_stream)))
+        out = []
+        for r in range(2):
+            streams[r].synchronize()
+            out.append((res[r][0].cpu().numpy().copy(), res[r][1].cpu().numpy().copy(), res[r][2].cpu().numpy().copy()))
+        return out
+
+    for ix in ixs:
+        ix.build()
+        ix.set_search_width(1)      # the one-warp walk is the kernel that pushes from its epilogue
+    plain = run(False)
+    for step in range(3):
+        fused = run(True)
+        for r in range(2):
+            for a, b in zip(plain[r], fused[r]):
+                assert np.array_equal(a, b), (step, r)
+    assert np.array_equal(plain[0][0], plain[1][0])             # both ranks hold the same global top-k
+    assert recall(plain[0][0].view(np.uint64), ref) >= 0.9
+    for r in range(2):
+        t = C.c_uint32()
+        check(L.ehb_exchange_timed_out(exs[r], C.byref(t)))
+        assert t.value == 0
     for h in exs:
         L.ehb_exchange_destroy(h)
