@@ -400,6 +400,8 @@ def run_ehb(args, wl):
 
     # ---- build the shard (setup, untimed): generated chunk by chunk, added as it comes -----------------
     ix = ehb.NativeIndex(d, metric=metric, capacity=N, device=local)
+    if args.walk_prefetch >= 0:
+        ix.set_option("walk_prefetch", args.walk_prefetch)
     t0 = time.time()
     for first, x in prefetched(gen_chunks(N, d, BASE_SEED + 1000 * rank)):
         ix.add(x, np.arange(rank * N + first, rank * N + first + x.shape[0], dtype=np.uint64))  # global labels
@@ -694,6 +696,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--walk-prefetch", type=int, default=-1, help="A/B: 0/1 sets the library option, -1 keeps its default")
     ap.add_argument("--parity-budget", type=float, default=45.0, help="seconds of CPU construction for the parity block")
     ap.add_argument("--ref-build-budget", type=float, default=100.0)
     ap.add_argument("--ref-max-points", type=int, default=1_000_000)

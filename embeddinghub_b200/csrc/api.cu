@@ -50,6 +50,7 @@ ehb::WalkCfg ehb_index::walk_cfg(uint32_t ef_eff, uint32_t smem_list, uint64_t j
   c.lcap = smem_list;
   c.staged = dpad > 256 ? 1 : 0;  // rows above 1 KB go through the TMA staging ring
   c.dcap = n_deleted ? ehb::kDeletedQueue : 0;
+  c.prefetch = o_walk_prefetch ? 1 : 0;
   // dense walk (search_impl.cuh): batches big enough to fill 20 warps per SM, rows <= 512 B, no tombstones
   c.dense = (!smem_list && team == 1 && !c.staged && dpad <= 128 && !n_deleted && jobs >= 20ull * (uint64_t)sms) ? 1 : 0;
   const uint32_t warp_target = c.dense ? 20u : 16u;  // resident warps per SM the visited-table sizing aims at
@@ -1010,6 +1011,8 @@ int ehb_index_set_option(ehb_index* ix, const char* name, int64_t value) {
     ix->o_bf16_unfused = value != 0;
   } else if (o == "gemm_2cta") {
     ix->o_gemm_2cta = value != 0;
+  } else if (o == "walk_prefetch") {
+    ix->o_walk_prefetch = value != 0;
   } else if (o == "combine") {
     ix->o_combine = value != 0;
   } else {

@@ -264,6 +264,7 @@ struct ehb_index {
   bool o_bf16_unfused = false;   // bf16 brute force: keep the distance tiles in HBM (A/B)
   bool o_gemm_2cta = false;      // bf16 brute force: cta_group::2 cluster form of the fused GEMM
   bool o_combine = true;         // coalesce concurrent small host searches
+  bool o_walk_prefetch = true;   // L2 prefetch of the speculated next hop's vectors (rows <= 1 KB)
 
   std::default_random_engine level_rng;
 

@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(T * 32, (T == 4 && U * NQ >= 16) ? 3 : 7) hnsw
   c.cand_dist = cand_dist + w * 32;
   c.keys = nullptr;
   c.cnt = 0;
+  c.dcap = 0;
+  c.prefetch = 0;
 
   for (uint32_t i = tid; i < hash_size; i += T * 32) hash[i] = kInvalid;
   if (tid < 8) misc[tid] = 0;

@@ -46,6 +46,7 @@ struct WalkCfg {
   uint32_t NG;         // staging groups (ring depth, <= 8)
   uint32_t staged;     // 1 when the TMA staging ring is allocated
   uint32_t dense;      // 1: launch the low-register form of the walk (more resident warps; rows <= 512 B only)
+  uint32_t prefetch;   // 1: pull the speculated next hop's vectors towards L2 (rows <= 1 KB)
   uint32_t dcap;       // capacity of the side queue of admitted-but-deleted candidates (0 = index has no tombstones)
 };
 
@@ -95,7 +96,7 @@ struct WarpCtx {
   uint32_t* dq_hi;   // deleted-candidate queue (unordered), see beam_search
   uint32_t* dq_id;
   float* stage;
-  uint32_t lcap, hsize, G, NG, dpad, vbytes, dcap;
+  uint32_t lcap, hsize, G, NG, dpad, vbytes, dcap, prefetch;
   uint32_t phases;  // one parity bit per staging group
   uint32_t cnt;     // live entries in keys[] (shared-memory list only)
   uint32_t lane;
@@ -121,6 +122,7 @@ __device__ __forceinline__ void ctx_init(WarpCtx& c, unsigned char* base, const 
   c.mbar = (uint64_t*)p;
   p += 128;
   c.dcap = cfg.dcap;
+  c.prefetch = cfg.prefetch;
   c.dq_hi = (uint32_t*)p;
   c.dq_id = c.dq_hi + cfg.dcap;
   p += align_up(cfg.dcap * 8u, 128);
@@ -636,7 +638,7 @@ __device__ __forceinline__ void beam_search(WarpCtx& c, const GraphView& g, cons
       eval_candidates<LPV, NQ, UDIV>(c, g.vecs, qr, m, g.metric);
       // the speculative row has arrived by now: pull its neighbours' vectors towards L2 while this hop's
       // candidates are inserted (rows <= 1 KB only; a wrong guess costs bandwidth, not correctness)
-      if (PREFETCH && LPV == 8 && spec_row != kInvalid) {
+      if (PREFETCH && LPV == 8 && c.prefetch && spec_row != kInvalid) {
         const char* pv = (const char*)(g.vecs + (size_t)spec_row * g.dpad);
 #pragma unroll
         for (int b = 0; b < NQ * 8 * 16; b += 128) prefetch_l2(pv + b);
