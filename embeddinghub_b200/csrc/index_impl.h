@@ -264,7 +264,10 @@ struct ehb_index {
   bool o_bf16_unfused = false;   // bf16 brute force: keep the distance tiles in HBM (A/B)
   bool o_gemm_2cta = false;      // bf16 brute force: cta_group::2 cluster form of the fused GEMM
   bool o_combine = true;         // coalesce concurrent small host searches
-  bool o_walk_prefetch = true;   // L2 prefetch of the speculated next hop's vectors (rows <= 1 KB)
+  // L2 prefetch of the speculated next hop's vectors (rows <= 1 KB).  Off: on the full C5 shard ncu showed 52.7 GB
+  // of DRAM traffic for 41.4 GB algorithmic (already-visited neighbours and wrong guesses are fetched too) and
+  // the walk is 5.9 % faster without it (10.43 -> 9.82 ms); r1 had measured no gain at C2 either.
+  bool o_walk_prefetch = false;
 
   std::default_random_engine level_rng;
 
