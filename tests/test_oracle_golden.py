@@ -129,3 +129,56 @@ def test_parallel_build_and_graph_roundtrip():
     h2.import_graph(g)
     b = h2.search(q, 10, ef=50)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+# hnswlib markDelete / has_deletions search / addPoint of a deleted label (the delete the reference's docs
+# promise, docs/reading_and_writing_embeddings.md:49-66): the checker's own semantics, pinned on the CPU
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_oracle_tombstones(metric):
+    rng = np.random.default_rng(3)
+    n, d, k = 3000, 24, 10
+    base = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((50, d)).astype(np.float32)
+    o = orc.OracleHNSW(d, metric, n)
+    o.add(base, threads=1)
+    before, _, _ = o.search(q, k, ef=200)
+    dead = np.unique(before[:, 0])                      # delete every query's nearest neighbour
+    for l in dead:
+        o.mark_delete(int(l))
+    assert o.deleted_count == len(dead)
+    with pytest.raises(RuntimeError):
+        o.mark_delete(int(dead[0]))                     # "already deleted"
+    with pytest.raises(KeyError):
+        o.mark_delete(n + 1)                            # "Label not found"
+    with pytest.raises(KeyError):
+        o.get(int(dead[0]))
+    after, dist, cnt = o.search(q, k, ef=200)
+    assert np.all(cnt == k) and not np.isin(after, dead).any()
+    alive = np.setdiff1d(np.arange(n, dtype=np.uint64), dead)
+    ref, _ = orc.bruteforce(base[alive.astype(np.int64)], q, k, metric)
+    ref = alive[ref.astype(np.int64)]
+    rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(after, ref)])
+    assert rec >= 0.95, rec                             # tombstones are traversed: recall over the survivors holds
+    # re-adding a deleted label brings it back at its new place
+    o.add(q[:1], np.array([dead[0]], np.uint64), threads=1)
+    assert o.deleted_count == len(dead) - 1
+    hit, _, _ = o.search(q[:1], 1, ef=200)
+    assert int(hit[0, 0]) == int(dead[0])
+
+
+def test_reference_arm_runs_on_cpu():
+    """bench.py --impl reference (the oracle end to end, calibrated and pinned threads) stays runnable without a
+    GPU; tiny budget."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c2s",
+                          "--steps", "2", "--warmup", "1", "--ref-build-budget", "3"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "queries/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["pinned"] is True
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and 0.0 < line["recall_at_k"] <= 1.0
