@@ -87,6 +87,8 @@ class ShardedSearcher:
         if self._ex is not None and nq <= self._ex_cap[0] and k <= self._ex_cap[1]:
             return
         t.cuda.synchronize()
+        if self._ex is not None:
+            dist.barrier(group=self.group)   # no peer may still be storing into the buffer that is about to go
         self.close()
         cap = (max(nq, self._ex_cap[0]), max(k, self._ex_cap[1]))
         rank = dist.get_rank(self.group)
