@@ -52,3 +52,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f in ("walk.cuh", "bruteforce.cu"), f
+
+
+def test_rwlock_stress_host_only():
+    """ehb::RwLock (writers preferred) under 8 spinning readers: exclusion holds and no writer starves.  Host code
+    only, so it runs in the CPU tier."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "tests", "cpp", "rwlock_stress")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/rwlock_stress not built (make)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
