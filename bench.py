@@ -112,6 +112,12 @@ def prefetched(it, depth=2):
         yield item
 
 
+def shared_config(wl, world):
+    """`config` of a bench line: identical for the GPU arm and the reference arm of one workload / rank count."""
+    return {"workload": wl["desc"], "N_per_gpu": wl["N"], "N_total": wl["N"] * world, "d": wl["d"], "Q": wl["Q"],
+            "k": wl["k"], "ef": wl["ef"], "metric_space": wl["metric"], "M": 16, "ef_construction": 200}
+
+
 def recall_at_k(found, truth):
     k = truth.shape[1]
     return float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(found, truth)]))
@@ -325,8 +331,10 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "k-NN queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "N": N, "N_sample": built, "d": d, "Q": Q, "k": k, "ef": ef,
-                   "metric_space": wl["metric"]},
+        # the same `config` dict as the GPU arm prints for this workload and rank count; arm-specific facts
+        # (the sub-sample the CPU graph was built over) go to `details`
+        "config": shared_config(wl, max(args.gpus, 1)),
+        "details": {"N_sample": built, "graph": "CPU-built by the oracle over a time-bounded prefix of the same base stream"},
         "recall_at_k": rec,
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
                          "best_queries_per_s": (Qs if not brute else qs * ns / N) / best, "build_s": round(t_build, 1),
@@ -661,12 +669,12 @@ def run_ehb(args, wl):
         "metric": "k-NN queries/s", "value": global_qps, "unit": "queries/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic" if DIST == "gaussian" else "synthetic (gmm)",
-        "config": {"workload": wl["desc"], "N_per_gpu": N, "N_total": N * world, "d": d, "Q": Q, "k": k, "ef": ef,
-                   "metric_space": metric, "M": 16, "ef_construction": 200, "path": "bruteforce bf16 tcgen05 + fp32 re-rank" if brute else "graph walk", "l2": "flushed between timed steps "
-                   "(256 MB write) and the index (vectors+links) is larger than L2", "parallelism":
-                   f"range-sharded x{world}, one {searcher.exchange} exchange of per-shard top-k + merge" if world > 1 else "single GPU",
-                   "exchange": searcher.exchange, "build_s": round(t_build, 2), "ingest_s": round(t_ingest, 1),
-                   "setup_s": round(time.time() - t_setup0, 1)},
+        "config": shared_config(wl, world),
+        "details": {"path": "bruteforce bf16 tcgen05 + fp32 re-rank" if brute else "graph walk",
+                    "l2": "flushed between timed steps (256 MB write) and the index (vectors+links) is larger than L2",
+                    "parallelism": f"range-sharded x{world}, one {searcher.exchange} exchange of per-shard top-k + merge"
+                    if world > 1 else "single GPU", "exchange": searcher.exchange, "build_s": round(t_build, 2),
+                    "ingest_s": round(t_ingest, 1), "setup_s": round(time.time() - t_setup0, 1)},
         "shard_searches_per_s": world * global_qps,
         "shard_only_ms_per_step": shard_ms,
         "recall_at_k": rec, "recall_queries": nrec,
